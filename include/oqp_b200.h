@@ -1,0 +1,125 @@
+/*
+ * oqp_b200.h -- C ABI of libopenqp_b200.so, a B200 (sm_100a) direct-SCF two-electron J/K Fock builder
+ * that drops in for OpenQP's `int2` driver and its J/K consumers.
+ *
+ * Conventions (identical to the reference's existing GPU seam, source/modules/routec_bridge.F90:30-41):
+ *   - plain C, `extern "C"`, host pointers unless the name ends in `_dev`, caller owns every array,
+ *     nothing is retained past return except what the ctx caches (basis, pair table, Schwarz matrix);
+ *   - every entry returns `info` (also stored through the trailing `int* info` of the legacy symbol):
+ *     0 = success, anything else = "not handled" -> the Fortran caller silently runs its native path
+ *     (routec_bridge.F90:258-263).  There is NO CPU fallback inside this library: without a CUDA device
+ *     every compute entry returns OQPB_ERR_NO_DEVICE.
+ *   - matrices: packed lower-triangular `ij = i(i-1)/2 + j` (1-based, i >= j) for SCF densities/Focks
+ *     (int2.F90:1436-1447); column-major nbf x nbf for response densities (tdhf_lib.F90:13-15);
+ *     d3/f3(nvec, ncomp, nbf, nbf) with nvec fastest for MRSF (tdhf_mrsf_lib.F90:10-11).
+ *   - shell/AO indices in `oqpb_set_basis` are 0-based offsets (subtract 1 from the Fortran arrays).
+ *
+ * Each entry cites the reference interface it replaces.
+ */
+#ifndef OQP_B200_H
+#define OQP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct oqpb_ctx oqpb_ctx;
+
+enum {
+  OQPB_OK = 0,
+  OQPB_ERR_NO_DEVICE = 1,   /* no CUDA device / driver: caller must use its native path            */
+  OQPB_ERR_BAD_ARG = 2,
+  OQPB_ERR_UNSUPPORTED = 3, /* L > 3, mixed harmonic flags inside one L, nbf too large, ...         */
+  OQPB_ERR_STATE = 4,       /* call order violated (basis / cutoff / screening not set)            */
+  OQPB_ERR_CUDA = 5         /* a CUDA runtime call failed; see oqpb_last_error()                    */
+};
+
+/* flags of oqpb_jk_td: fields of int2_td_data_t, tdhf_lib.F90:11-31 */
+enum { OQPB_TD_APB = 1, OQPB_TD_AMB = 2, OQPB_TD_TDA = 4, OQPB_TD_TDA_COULOMB = 8 };
+
+/* ---- lifetime: replaces int2_compute_t construction/clean (int2.F90:137-185, 245-289) ------------- */
+int  oqpb_ctx_create(oqpb_ctx** ctx, int device);
+void oqpb_ctx_destroy(oqpb_ctx* ctx);
+const char* oqpb_last_error(const oqpb_ctx* ctx);
+
+/* The arrays of `basis_set` (basis_tools.F90:32-51) after normalize_primitives (:277-303):
+ * am, harmonic, ncontr, g_offset, ao_offset, naos [nshell]; ex, cc [nprim]; centers [3*nshell] (Bohr,
+ * = shell_centers, basis_tools.F90:1316-1326).  harmonic_active = constants.F90 HARMONIC_ACTIVE.      */
+int oqpb_set_basis(oqpb_ctx* ctx, int nshell, int nprim, const int* am, const int* harmonic,
+                   const int* ncontr, const int* g_offset, const int* ao_offset, const int* naos,
+                   const double* ex, const double* cc, const double* centers, int harmonic_active);
+
+/* int2_compute_t%init cutoffs + %set_cutoff (int2.F90:260-272; int2_pairs.F90:285-294):
+ * integral = c, pair = 1e-2 c, quartet = 1e-4 c, exponent = 25 ln 10.  (Re)builds the device pair table. */
+int oqpb_set_cutoff(oqpb_ctx* ctx, double cutoff);
+
+/* int2_compute_t%set_screening -> ints_exchange (int2.F90:473-477, 1582-1737).
+ * schwarz_in == NULL: compute Q_ij = sqrt(max|(ij|ij)|) on the device with the reference's tight cutoffs
+ * (1e-15, 1e-17, 1e-17, 50); otherwise upload the caller's nshell x nshell matrix (bit-exact screening
+ * against a host-computed Q).  Sorts the pair lists by Q for the quartet enumeration.                   */
+int oqpb_set_screening(oqpb_ctx* ctx, const double* schwarz_in);
+int oqpb_get_schwarz(oqpb_ctx* ctx, double* schwarz_out /* nshell*nshell */);
+
+/* Multi-GPU / MPI replicated-data split of the bra shell-pair list, the reference's
+ * `mod(ij_pair, size) == rank` (int2.F90:759-761).  The caller sums the partial results
+ * (pe%allreduce, int2.F90:1396; NCCL all-reduce on the *_dev entry points).                           */
+int oqpb_set_partition(oqpb_ctx* ctx, int rank, int nranks);
+
+/* fock_jk (scf_addons.F90:1063-1214) = int2_rhf_data_t / int2_urohf_data_t consumers
+ * (int2.F90:1414-1578) + 0.5/diagonal post-scaling (:1177-1185) when `post` != 0:
+ *   RHF  (urohf = 0): f_m = sc*J[d_m] - 1/2 se*K[d_m],  m = 1..nfocks
+ *   UROHF(urohf = 1): f_s = sc*J[d_1+d_2] - se*K[d_s],   nfocks = 2
+ * d, f: packed (ntri, nfocks).  nskipped = int2_compute_t%skipped (nschwz).  Host pointers.           */
+int oqpb_fock(oqpb_ctx* ctx, int urohf, const double* d, double* f, int nfocks, double scale_exchange,
+              double scale_coulomb, int post, long long* nskipped);
+/* same with DEVICE pointers, asynchronous on the ctx stream, no host copies: the result stays in HBM
+ * for the caller's NCCL all-reduce; oqpb_fock_post_dev applies the 0.5/diag scaling afterwards.       */
+int oqpb_fock_dev(oqpb_ctx* ctx, int urohf, const double* d_dev, double* f_dev, int nfocks,
+                  double scale_exchange, double scale_coulomb);
+int oqpb_fock_post_dev(oqpb_ctx* ctx, double* f_dev, int nfocks);
+int oqpb_synchronize(oqpb_ctx* ctx);
+void* oqpb_stream(oqpb_ctx* ctx); /* cudaStream_t the ctx launches on */
+
+/* int2_td_data_t (tdhf_lib.F90:11-31, update :140-224, parallel_stop symmetrisation :107-109):
+ * d2, apb, amb: column-major (nbf, nbf, nvec).  apb is returned symmetrised (apb + apb^T).            */
+int oqpb_jk_td(oqpb_ctx* ctx, const double* d2, int nvec, int flags, double scale_exchange,
+               double scale_coulomb, double* apb, double* amb, long long* nskipped);
+
+/* int2_mrsf_data_t (tdhf_mrsf_lib.F90:8-26, update :218-333), pass 1:
+ * f3(v,c,:,:) = sc*J[d3(v,c)] (c <= 4) - se*K[d3(v,c)] (all c); d3, f3: (nvec, ncomp, nbf, nbf).      */
+int oqpb_jk_mrsf(oqpb_ctx* ctx, const double* d3, int nvec, int ncomp, double scale_exchange,
+                 double scale_coulomb, double* f3, long long* nskipped);
+
+/* ---- introspection used by the parity tests and the benchmark ------------------------------------- */
+/* statistics of the last build: [0] surviving shell quartets, [1] skipped (nschwz), [2] primitive
+ * quartets evaluated is not tracked (0), [3] kernel launches, [4] algorithmic FLOPs (SURVEY 8d-1 model,
+ * as a double bit-cast is avoided: returned through oqpb_last_flops).                                  */
+int oqpb_last_stats(oqpb_ctx* ctx, long long* stats4);
+double oqpb_last_flops(oqpb_ctx* ctx);
+double oqpb_last_kernel_ms(oqpb_ctx* ctx); /* CUDA-event time of the ERI/digest kernels of the last build */
+/* surviving canonical shell quartets (i>=j, k>=l, (ij)>=(kl), 0-based) of the last build, unordered;
+ * returns the count, writes at most maxq quadruples.  Must be enabled before the build.               */
+int oqpb_record_quartets(oqpb_ctx* ctx, int enable);
+long long oqpb_get_quartets(oqpb_ctx* ctx, int* ijkl, long long maxq);
+/* shell-block max|D| of the last build (shlden, int2.F90:999-1047), nshell*nshell                     */
+int oqpb_get_shell_density(oqpb_ctx* ctx, double* dsh, double* max_den);
+/* one shell quartet (0-based, any order) -> unit-normalised, pure-projected block out(i,j,k,l), l fastest
+ * (shellquartet, int2.F90:1051-1183); nout[4] receives the block dimensions.                          */
+int oqpb_eri_block(oqpb_ctx* ctx, int i, int j, int k, int l, double* out, int* nout);
+/* Rys roots (as t^2) and weights from the device tables, for n <= 7 (rys_root_t%evaluate, rys.F90:24-36) */
+int oqpb_rys(oqpb_ctx* ctx, int nroots, int npts, const double* x, double* t2, double* w);
+/* measured FP64 FMA peak of this device in TFLOP/s (roofline denominator; MEASURED_PEAKS.json has none) */
+double oqpb_fp64_peak_tflops(oqpb_ctx* ctx);
+
+/* ---- legacy seam, identical signature to routec_bridge.F90:33-40 / 81-89 --------------------------- */
+/* Uses the process-global context registered with oqpb_set_default_ctx; RHF semantics for nfocks = 1,
+ * UROHF for nfocks = 2 unless overridden by oqpb_set_default_scftype.                                  */
+void routec_fock_jk(const double* d, double* f, const int* nbf, const int* nfocks, const double* scale_exchange,
+                    const double* scale_coulomb, int* info);
+int oqpb_set_default_ctx(oqpb_ctx* ctx);
+int oqpb_set_default_scftype(int urohf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

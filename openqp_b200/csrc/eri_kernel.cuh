@@ -1,0 +1,702 @@
+// Rys-quadrature ERI + fused J/K digestion kernels for sm_100a.
+//
+// One kernel per canonical angular-momentum class (LA>=LB | LC>=LD), bra class >= ket class, s..f.
+// Replaces, for one batch of surviving shell quartets, the reference's per-thread sequence
+//   shellquartet -> int2_rys_compute (int_rys.F90:156-276) -> normalize/pure projection
+//   (int2.F90:1187-1207, int_rys.F90:715-785) -> storeints (int2.F90:1741-1865) -> consumer update
+//   (int2.F90:1414-1578, tdhf_lib.F90:140-224, tdhf_mrsf_lib.F90:218-333).
+//
+// Mapping: a CTA owns QPB quartets; a quartet is owned by a team of TS = NA*NB*KS threads (one thread
+// per bra Cartesian component pair, optionally KS ket slices).  Per primitive quartet:
+//   B1  2R threads evaluate the Rys roots/weights (Chebyshev tables) into shared memory,
+//   B2  3R threads run the 2-D VRR and both HRR transfers for one (root, direction) each, in shared memory,
+//   B3  every thread accumulates its NC*ND/KS ket components in registers:  I += gx*gy*gz.
+// Then the Cartesian block goes to shared memory, is normalised / projected to pure functions index by
+// index (sparse tables), the element cutoff and the coincidence factors are applied, and the block is
+// contracted with the density: J and K partial sums are reduced in registers per output element and
+// leave the CTA as one FP64 red.global.add per Fock element per quartet.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <type_traits>
+#include <utility>
+
+namespace oqpb {
+
+struct PairEntry {
+  int sa, sb;      // shells, am(sa) >= am(sb); equal am: sa is the canonical row shell (sa >= sb)
+  int poff, pcnt;  // primitive-pair records
+};
+
+constexpr int PRIM_STRIDE = 5;  // Px Py Pz zeta K  (K = sqrt(2) pi^{5/4} c_a c_b exp(-ab R^2/zeta), int2_pairs.F90:259)
+
+constexpr int MAX_PROJ_TERMS = 6;
+struct ProjTable {  // output row -> sparse list over my internal Cartesian order (normalisation folded in)
+  int nout;
+  int nterm[10];
+  int idx[10][MAX_PROJ_TERMS];
+  double coef[10][MAX_PROJ_TERMS];
+};
+
+enum Mode { MODE_SYM = 0, MODE_GEN = 1, MODE_SCHWARZ = 2, MODE_BLOCK = 3 };
+
+constexpr int MAX_MATS = 8;
+
+struct EriArgs {
+  const PairEntry* bra;
+  const PairEntry* ket;
+  const double* prim;
+  const double* xyz;
+  const int* aooff;
+  const int2* tasks;
+  const unsigned* ntasks;  // device-resident count
+  unsigned* counter;       // dynamic task fetch
+  const double* rys_tab;   // table base for this nroots
+  int rys_xmax;
+  double herm_r[7], herm_w[7];
+  double prim_cutoff;  // pair_cutoff^2 (int_rys.F90:74,232)
+  double cutoff;       // element cutoff (int2.F90:1806-1812)
+  const ProjTable* proj;  // 4 tables (device memory): for la, lb, lc, ld
+  int mode;
+  int nbf;
+  // MODE_SYM: packed Fock accumulation, out_m += 4*cj*Jtype[DJ_m] - ck*Ktype[DK_m]   (reference's 6 updates)
+  int nmat;
+  const double* DJ[MAX_MATS];
+  const double* DK[MAX_MATS];
+  double* F[MAX_MATS];
+  double cj, ck;
+  // MODE_GEN: square general densities P_m (row-major [a*nbf+b] = P(a,b)); Jout_m/Kout_m square accumulators
+  //   Jout_m(a,b) += cj * v * (P(c,d)+P(d,c)), (c,d) likewise with (a,b);  Kout_m 8-target form with ck.
+  //   gen_wantj[m]: whether matrix m takes the Coulomb part.
+  int gen_wantj[MAX_MATS];
+  // batched GEN: matrices stored interleaved [a*nbf+b][nmat] when gen_interleaved != 0 (MRSF layout)
+  int gen_interleaved;
+  int gen_nmat_total;  // nmat for interleaved layout (may exceed MAX_MATS)
+  int gen_ncoul;       // interleaved: component index < gen_ncoul gets Coulomb (uses comp = m / nvec ... see kernel)
+  int gen_nvec;
+  const double* Pgen;  // interleaved density
+  double* Fgen;        // interleaved output
+  unsigned long long* stat;  // [0] += primitive quartets evaluated, [1] += 8 * sum(fac * surviving AO integrals)
+  // MODE_SCHWARZ
+  double* qout;  // per bra entry
+  // MODE_BLOCK
+  double* blockout;
+};
+
+__host__ __device__ constexpr int ncart(int l) { return (l + 1) * (l + 2) / 2; }
+
+// internal Cartesian order: x descending, then y descending
+template <int L>
+struct Cart {
+  static constexpr int N = (L + 1) * (L + 2) / 2;
+  __host__ __device__ static constexpr int x(int c) {
+    int k = 0;
+    for (int xx = L; xx >= 0; --xx)
+      for (int yy = L - xx; yy >= 0; --yy) {
+        if (k == c) return xx;
+        ++k;
+      }
+    return 0;
+  }
+  __host__ __device__ static constexpr int y(int c) {
+    int k = 0;
+    for (int xx = L; xx >= 0; --xx)
+      for (int yy = L - xx; yy >= 0; --yy) {
+        if (k == c) return yy;
+        ++k;
+      }
+    return 0;
+  }
+  __host__ __device__ static constexpr int z(int c) { return L - x(c) - y(c); }
+};
+
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+__device__ __forceinline__ void cart_xyz_rt(int l, int c, int& x, int& y, int& z) {
+  int k = 0;
+  x = y = z = 0;
+  for (int xx = l; xx >= 0; --xx)
+    for (int yy = l - xx; yy >= 0; --yy) {
+      if (k == c) { x = xx; y = yy; z = l - xx - yy; }
+      ++k;
+    }
+}
+
+template <int LA, int LB, int LC, int LD>
+struct ClassCfg {
+  static constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
+  static constexpr int R = (LA + LB + LC + LD) / 2 + 1;
+  static constexpr int NMAX = LA + LB + 1, MMAX = LC + LD + 1;
+  static constexpr int NIJ1 = (LA + 1) * (LB + 1), NKL1 = (LC + 1) * (LD + 1);
+  static constexpr int NKET = NC * ND;
+  static constexpr int KS = (NKET + 39) / 40;           // ket slices (<= 40 accumulators / thread)
+  static constexpr int TKC = (NC + KS - 1) / KS;        // ket-c components per slice
+  static constexpr int NACC = TKC * ND;
+  static constexpr int TS = NA * NB * KS;               // threads per quartet
+  static constexpr int G1 = NMAX * MMAX, G2 = NMAX * NKL1, G3 = NIJ1 * NKL1;
+  static constexpr int GSTR = (G1 + G2 + G3) | 1;       // odd stride: conflict-free across (root,dir) tasks
+  static constexpr int GREG = 3 * R * GSTR;
+  static constexpr int NCART4 = NA * NB * NC * ND;
+  static constexpr int BLK = 2 * NCART4;                // ping-pong for the index-wise projection
+  static constexpr int QSM0 = (GREG > BLK ? GREG : BLK) + 2 * R + 2;
+  static constexpr int QSM = QSM0 | 1;                  // doubles per quartet, odd
+  static constexpr int QPB_T = (288 / TS) > 0 ? (288 / TS) : 1;
+  static constexpr int QPB_S = (12288 / QSM) > 0 ? (12288 / QSM) : 1;  // <= 96 KB of dynamic smem per CTA
+  static constexpr int QPB = QPB_T < QPB_S ? QPB_T : QPB_S;
+  static constexpr int NT = ((TS * QPB + 31) / 32) * 32;
+  static constexpr size_t SMEM = (size_t)QPB * QSM * sizeof(double) + QPB * 64 * sizeof(int);
+};
+
+struct QInfo {  // 64 ints per quartet in shared memory
+  int sa, sb, sc, sd;
+  int boff, bcnt, koff, kcnt;
+  int oa, ob, oc, od;
+  int valid, nonzero, keep, pad;
+  float fac;
+  int bra_id, ket_id, pad2;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// roots / weights for function f (f < R: root t^2, f >= R: weight) at X
+template <int R>
+__device__ __forceinline__ double rys_eval(const EriArgs& a, double X, int f) {
+  if (X >= (double)a.rys_xmax) {
+    // half-range Gauss-Hermite asymptote (rys.F90:2711-2713)
+    if (f < R) return a.herm_r[f] / X;
+    return a.herm_w[f - R] * rsqrt(X);
+  }
+  int iv = (int)X;
+  double t = 2.0 * (X - (double)iv) - 1.0;
+  const double* c = a.rys_tab + ((size_t)iv * (2 * R) + f) * 12;
+  // Clenshaw
+  double b1 = 0.0, b2 = 0.0, t2 = 2.0 * t;
+#pragma unroll
+  for (int k = 11; k >= 1; --k) {
+    double b0 = fma(t2, b1, __ldg(c + k) - b2);
+    b2 = b1;
+    b1 = b0;
+  }
+  return fma(t, b1, __ldg(c) - b2);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// index-wise projection pass: in[(outer, j<nin, inner)] -> out[(outer, o<nout, inner)]
+__device__ __forceinline__ void proj_pass(const double* __restrict__ in, double* __restrict__ out, int outer, int nin,
+                                          int inner, const ProjTable& T, int t, int ts) {
+  const int nout = T.nout;
+  const int tot = outer * nout * inner;
+  for (int e = t; e < tot; e += ts) {
+    int i = e % inner;
+    int r = e / inner;
+    int o = r % nout;
+    int ou = r / nout;
+    const double* src = in + (size_t)ou * nin * inner + i;
+    double s = 0.0;
+    const int nt = T.nterm[o];
+    for (int k = 0; k < nt; ++k) s = fma(T.coef[o][k], src[T.idx[o][k] * inner], s);
+    out[e] = s;
+  }
+}
+
+__device__ __forceinline__ size_t tri_idx(int p, int q) {
+  return p >= q ? (size_t)p * (p + 1) / 2 + q : (size_t)q * (q + 1) / 2 + p;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Digestion of one finished block blk[a][b][c][d] (d fastest), dims n0..n3, AO offsets o0..o3.
+// MODE_SYM: the reference's six packed updates (int2.F90:1414-1484 / 1488-1578) on the full block
+// with the shell-level coincidence factor `fac` (equivalent to the unique-AO walk + AO-level halving of
+// storeints, int2.F90:1769-1851).
+__device__ __forceinline__ void digest_sym(const EriArgs& A, const double* blk, int n0, int n1, int n2, int n3, int o0,
+                                           int o1, int o2, int o3, int t, int ts) {
+  const int nbf = A.nbf;
+  const int n23 = n2 * n3, n123 = n1 * n23;
+  const double c4 = 4.0 * A.cj, c1 = A.ck;
+  for (int m = 0; m < A.nmat; ++m) {
+    const double* __restrict__ DJ = A.DJ[m];
+    const double* __restrict__ DK = A.DK[m];
+    double* __restrict__ F = A.F[m];
+    // J_ab += 4 cj sum_cd v D_cd
+    for (int o = t; o < n0 * n1; o += ts) {
+      int a = o / n1, b = o % n1;
+      const double* v = blk + (size_t)o * n23;
+      double s = 0.0;
+      for (int c = 0; c < n2; ++c) {
+        const double* drow = DJ + (size_t)(o2 + c) * nbf + o3;
+        for (int d = 0; d < n3; ++d) s = fma(v[c * n3 + d], __ldg(drow + d), s);
+      }
+      if (s != 0.0) atomicAdd(F + tri_idx(o0 + a, o1 + b), c4 * s);
+    }
+    // J_cd += 4 cj sum_ab v D_ab
+    for (int o = t; o < n23; o += ts) {
+      int c = o / n3, d = o % n3;
+      double s = 0.0;
+      for (int a = 0; a < n0; ++a) {
+        const double* drow = DJ + (size_t)(o0 + a) * nbf + o1;
+        for (int b = 0; b < n1; ++b) s = fma(blk[(size_t)(a * n1 + b) * n23 + o], __ldg(drow + b), s);
+      }
+      if (s != 0.0) atomicAdd(F + tri_idx(o2 + c, o3 + d), c4 * s);
+    }
+    // K_ac -= ck sum_bd v D_bd
+    for (int o = t; o < n0 * n2; o += ts) {
+      int a = o / n2, c = o % n2;
+      double s = 0.0;
+      for (int b = 0; b < n1; ++b) {
+        const double* drow = DK + (size_t)(o1 + b) * nbf + o3;
+        const double* v = blk + (size_t)(a * n1 + b) * n23 + c * n3;
+        for (int d = 0; d < n3; ++d) s = fma(v[d], __ldg(drow + d), s);
+      }
+      if (s != 0.0) atomicAdd(F + tri_idx(o0 + a, o2 + c), -c1 * s);
+    }
+    // K_ad -= ck sum_bc v D_bc
+    for (int o = t; o < n0 * n3; o += ts) {
+      int a = o / n3, d = o % n3;
+      double s = 0.0;
+      for (int b = 0; b < n1; ++b) {
+        const double* drow = DK + (size_t)(o1 + b) * nbf + o2;
+        const double* v = blk + (size_t)(a * n1 + b) * n23 + d;
+        for (int c = 0; c < n2; ++c) s = fma(v[c * n3], __ldg(drow + c), s);
+      }
+      if (s != 0.0) atomicAdd(F + tri_idx(o0 + a, o3 + d), -c1 * s);
+    }
+    // K_bc -= ck sum_ad v D_ad
+    for (int o = t; o < n1 * n2; o += ts) {
+      int b = o / n2, c = o % n2;
+      double s = 0.0;
+      for (int a = 0; a < n0; ++a) {
+        const double* drow = DK + (size_t)(o0 + a) * nbf + o3;
+        const double* v = blk + (size_t)(a * n1 + b) * n23 + c * n3;
+        for (int d = 0; d < n3; ++d) s = fma(v[d], __ldg(drow + d), s);
+      }
+      if (s != 0.0) atomicAdd(F + tri_idx(o1 + b, o2 + c), -c1 * s);
+    }
+    // K_bd -= ck sum_ac v D_ac
+    for (int o = t; o < n1 * n3; o += ts) {
+      int b = o / n3, d = o % n3;
+      double s = 0.0;
+      for (int a = 0; a < n0; ++a) {
+        const double* drow = DK + (size_t)(o0 + a) * nbf + o2;
+        const double* v = blk + (size_t)(a * n1 + b) * n23 + d;
+        for (int c = 0; c < n2; ++c) s = fma(v[c * n3], __ldg(drow + c), s);
+      }
+      if (s != 0.0) atomicAdd(F + tri_idx(o1 + b, o3 + d), -c1 * s);
+    }
+  }
+  (void)n123;
+}
+
+// MODE_GEN: general (non-symmetric) densities, all 8 permutations (tdhf_lib.F90:173-186,
+// tdhf_mrsf_lib.F90:279-310).  Matrices interleaved in the reference's MRSF layout d3(m, mu, nu):
+// X[(nu*nbf + mu)*NM + m] = X_m(mu,nu).
+//   Coulomb (m with comp < ncoul): F(a,b),F(b,a) += cj v (P(c,d)+P(d,c)); F(c,d),F(d,c) += cj v (P(a,b)+P(b,a))
+//   Exchange (all m): F(a,c) -= ck v P(b,d); F(c,a) -= ck v P(d,b); F(a,d) -= ck v P(b,c); F(d,a) -= ck v P(c,b);
+//                     F(b,c) -= ck v P(a,d); F(c,b) -= ck v P(d,a); F(b,d) -= ck v P(a,c); F(d,b) -= ck v P(c,a)
+// Threads are spread over (output element, matrix): m fastest -> coalesced density reads and atomics.
+__device__ __forceinline__ void digest_gen(const EriArgs& A, const double* blk, int n0, int n1, int n2, int n3, int o0,
+                                           int o1, int o2, int o3, int t, int ts) {
+  const int nbf = A.nbf, NM = A.gen_nmat_total, nv = A.gen_nvec;
+  const int n23 = n2 * n3;
+  const double* __restrict__ P = A.Pgen;
+  double* __restrict__ F = A.Fgen;
+  const int ncm = A.gen_ncoul * nv;  // interleaved index m = comp*nvec + v ... Coulomb for m < ncoul*nvec
+  const double cj = A.cj, ck = A.ck;
+#define PX(p, q) __ldg(P + ((size_t)(q)*nbf + (p)) * NM + m)
+#define FX(p, q, val) atomicAdd(F + ((size_t)(q)*nbf + (p)) * NM + m, (val))
+  if (ncm > 0 && cj != 0.0) {
+    for (int e = t; e < n0 * n1 * ncm; e += ts) {
+      int m = e % ncm, o = e / ncm;
+      int a = o / n1, b = o % n1;
+      const double* v = blk + (size_t)o * n23;
+      double s = 0.0;
+      for (int c = 0; c < n2; ++c)
+        for (int d = 0; d < n3; ++d) s = fma(v[c * n3 + d], PX(o2 + c, o3 + d) + PX(o3 + d, o2 + c), s);
+      if (s != 0.0) {
+        FX(o0 + a, o1 + b, cj * s);
+        FX(o1 + b, o0 + a, cj * s);
+      }
+    }
+    for (int e = t; e < n23 * ncm; e += ts) {
+      int m = e % ncm, o = e / ncm;
+      int c = o / n3, d = o % n3;
+      double s = 0.0;
+      for (int a = 0; a < n0; ++a)
+        for (int b = 0; b < n1; ++b)
+          s = fma(blk[(size_t)(a * n1 + b) * n23 + o], PX(o0 + a, o1 + b) + PX(o1 + b, o0 + a), s);
+      if (s != 0.0) {
+        FX(o2 + c, o3 + d, cj * s);
+        FX(o3 + d, o2 + c, cj * s);
+      }
+    }
+  }
+  if (ck != 0.0) {
+    for (int e = t; e < n0 * n2 * NM; e += ts) {  // (a,c)
+      int m = e % NM, o = e / NM;
+      int a = o / n2, c = o % n2;
+      double s1 = 0.0, s2 = 0.0;
+      for (int b = 0; b < n1; ++b) {
+        const double* v = blk + (size_t)(a * n1 + b) * n23 + c * n3;
+        for (int d = 0; d < n3; ++d) {
+          s1 = fma(v[d], PX(o1 + b, o3 + d), s1);
+          s2 = fma(v[d], PX(o3 + d, o1 + b), s2);
+        }
+      }
+      if (s1 != 0.0) FX(o0 + a, o2 + c, -ck * s1);
+      if (s2 != 0.0) FX(o2 + c, o0 + a, -ck * s2);
+    }
+    for (int e = t; e < n0 * n3 * NM; e += ts) {  // (a,d)
+      int m = e % NM, o = e / NM;
+      int a = o / n3, d = o % n3;
+      double s1 = 0.0, s2 = 0.0;
+      for (int b = 0; b < n1; ++b) {
+        const double* v = blk + (size_t)(a * n1 + b) * n23 + d;
+        for (int c = 0; c < n2; ++c) {
+          s1 = fma(v[c * n3], PX(o1 + b, o2 + c), s1);
+          s2 = fma(v[c * n3], PX(o2 + c, o1 + b), s2);
+        }
+      }
+      if (s1 != 0.0) FX(o0 + a, o3 + d, -ck * s1);
+      if (s2 != 0.0) FX(o3 + d, o0 + a, -ck * s2);
+    }
+    for (int e = t; e < n1 * n2 * NM; e += ts) {  // (b,c)
+      int m = e % NM, o = e / NM;
+      int b = o / n2, c = o % n2;
+      double s1 = 0.0, s2 = 0.0;
+      for (int a = 0; a < n0; ++a) {
+        const double* v = blk + (size_t)(a * n1 + b) * n23 + c * n3;
+        for (int d = 0; d < n3; ++d) {
+          s1 = fma(v[d], PX(o0 + a, o3 + d), s1);
+          s2 = fma(v[d], PX(o3 + d, o0 + a), s2);
+        }
+      }
+      if (s1 != 0.0) FX(o1 + b, o2 + c, -ck * s1);
+      if (s2 != 0.0) FX(o2 + c, o1 + b, -ck * s2);
+    }
+    for (int e = t; e < n1 * n3 * NM; e += ts) {  // (b,d)
+      int m = e % NM, o = e / NM;
+      int b = o / n3, d = o % n3;
+      double s1 = 0.0, s2 = 0.0;
+      for (int a = 0; a < n0; ++a) {
+        const double* v = blk + (size_t)(a * n1 + b) * n23 + d;
+        for (int c = 0; c < n2; ++c) {
+          s1 = fma(v[c * n3], PX(o0 + a, o2 + c), s1);
+          s2 = fma(v[c * n3], PX(o2 + c, o0 + a), s2);
+        }
+      }
+      if (s1 != 0.0) FX(o1 + b, o3 + d, -ck * s1);
+      if (s2 != 0.0) FX(o3 + d, o1 + b, -ck * s2);
+    }
+  }
+#undef PX
+#undef FX
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <int LA, int LB, int LC, int LD>
+__global__ void __launch_bounds__(ClassCfg<LA, LB, LC, LD>::NT)
+eri_kernel(const EriArgs A) {
+  using Cfg = ClassCfg<LA, LB, LC, LD>;
+  constexpr int R = Cfg::R, TS = Cfg::TS, QPB = Cfg::QPB, NA = Cfg::NA, NB = Cfg::NB, NC = Cfg::NC, ND = Cfg::ND;
+  constexpr int NMAX = Cfg::NMAX, MMAX = Cfg::MMAX, NKL1 = Cfg::NKL1, KS = Cfg::KS, TKC = Cfg::TKC;
+  constexpr int G1 = Cfg::G1, G2 = Cfg::G2, GSTR = Cfg::GSTR, QSM = Cfg::QSM;
+
+  extern __shared__ double smem[];
+  QInfo* qinfo = reinterpret_cast<QInfo*>(smem + (size_t)QPB * QSM);
+  __shared__ int s_maxk;
+  __shared__ unsigned s_base;
+
+  const int tid = threadIdx.x;
+  const int q = tid / TS;   // local quartet
+  const int t = tid % TS;   // team lane
+  const bool team_ok = q < QPB;
+  double* qs = smem + (size_t)(team_ok ? q : 0) * QSM;
+  double* rw = qs + (QSM - 2 * R - 1);   // roots/weights live at the tail of the quartet region
+  QInfo& qi = qinfo[team_ok ? q : 0];
+
+  // thread's bra component
+  const int tab = t / KS, slice = t % KS;
+  const int ia = tab / NB, ib = tab % NB;
+  int ax, ay, az, bx, by, bz;
+  cart_xyz_rt(LA, ia, ax, ay, az);
+  cart_xyz_rt(LB, ib, bx, by, bz);
+  const int obx = (ax * (LB + 1) + bx) * NKL1, oby = (ay * (LB + 1) + by) * NKL1, obz = (az * (LB + 1) + bz) * NKL1;
+
+  const unsigned ntasks = *A.ntasks;
+  const ProjTable* PT = A.proj;
+  unsigned long long st_prim = 0, st_ints = 0;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      s_base = atomicAdd(A.counter, (unsigned)QPB);
+      s_maxk = 0;
+    }
+    __syncthreads();
+    const unsigned base = s_base;
+    if (base >= ntasks) break;
+
+    // ---- setup
+    if (team_ok && t == 0) {
+      unsigned ti = base + q;
+      qi.valid = ti < ntasks;
+      qi.nonzero = 0;
+      if (qi.valid) {
+        int2 tk = A.tasks[ti];
+        PairEntry pb = A.bra[tk.x], pk = A.ket[tk.y];
+        qi.sa = pb.sa; qi.sb = pb.sb; qi.sc = pk.sa; qi.sd = pk.sb;
+        qi.boff = pb.poff; qi.bcnt = pb.pcnt; qi.koff = pk.poff; qi.kcnt = pk.pcnt;
+        qi.oa = A.aooff[pb.sa]; qi.ob = A.aooff[pb.sb]; qi.oc = A.aooff[pk.sa]; qi.od = A.aooff[pk.sb];
+        qi.bra_id = tk.x; qi.ket_id = tk.y;
+        float f = 1.0f;
+        if (pb.sa == pb.sb) f *= 0.5f;
+        if (pk.sa == pk.sb) f *= 0.5f;
+        if ((pb.sa == pk.sa && pb.sb == pk.sb) || (pb.sa == pk.sb && pb.sb == pk.sa)) f *= 0.5f;
+        qi.fac = f;
+        atomicMax(&s_maxk, pb.pcnt * pk.pcnt);
+      }
+    }
+    __syncthreads();
+    const int maxk = s_maxk;
+    const bool valid = team_ok && qi.valid;
+    const int bcnt = valid ? qi.bcnt : 1, nprimq = valid ? qi.bcnt * qi.kcnt : 0;
+    double Ax = 0, Ay = 0, Az = 0, Cx = 0, Cy = 0, Cz = 0, ABx = 0, ABy = 0, ABz = 0, CDx = 0, CDy = 0, CDz = 0;
+    if (valid) {
+      const double* xa = A.xyz + 3 * qi.sa; const double* xb = A.xyz + 3 * qi.sb;
+      const double* xc = A.xyz + 3 * qi.sc; const double* xd = A.xyz + 3 * qi.sd;
+      Ax = xa[0]; Ay = xa[1]; Az = xa[2]; Cx = xc[0]; Cy = xc[1]; Cz = xc[2];
+      ABx = Ax - xb[0]; ABy = Ay - xb[1]; ABz = Az - xb[2];
+      CDx = Cx - xd[0]; CDy = Cy - xd[1]; CDz = Cz - xd[2];
+    }
+
+    double acc[Cfg::NACC];
+#pragma unroll
+    for (int k = 0; k < Cfg::NACC; ++k) acc[k] = 0.0;
+    bool any = false;
+
+    for (int ip = 0; ip < maxk; ++ip) {
+      const bool act = ip < nprimq;
+      // primitive pair records (ket outer, bra inner: int_rys.F90:214-220)
+      double Px = 0, Py = 0, Pz = 0, zeta = 1, Kp = 0, Qx = 0, Qy = 0, Qz = 0, eta = 1, Kq = 0;
+      if (act) {
+        const double* pp = A.prim + (size_t)(qi.boff + ip % bcnt) * PRIM_STRIDE;
+        const double* pq = A.prim + (size_t)(qi.koff + ip / bcnt) * PRIM_STRIDE;
+        Px = __ldg(pp); Py = __ldg(pp + 1); Pz = __ldg(pp + 2); zeta = __ldg(pp + 3); Kp = __ldg(pp + 4);
+        Qx = __ldg(pq); Qy = __ldg(pq + 1); Qz = __ldg(pq + 2); eta = __ldg(pq + 3); Kq = __ldg(pq + 4);
+      }
+      const double ab = zeta + eta;
+      const double pfac = (Kp / zeta) * (Kq / eta);
+      // primitive-quartet screening, int_rys.F90:229-232
+      const bool keep = act && !(pfac * pfac < A.prim_cutoff * ab);
+      const double abinv = 1.0 / ab;
+      const double rho = zeta * eta * abinv;
+      const double PQx = Px - Qx, PQy = Py - Qy, PQz = Pz - Qz;
+      const double X = rho * (PQx * PQx + PQy * PQy + PQz * PQz);
+      // ---- B1: roots and weights
+      if (keep) {
+        for (int f = t; f < 2 * R; f += TS) rw[f] = rys_eval<R>(A, X, f);
+      }
+      __syncthreads();
+      // ---- B2: 2-D recurrences, one (root, direction) per thread
+      if (keep) {
+        const double pref = pfac * sqrt(abinv);
+        for (int task = t; task < 3 * R; task += TS) {
+          const int r = task / 3, dir = task % 3;
+          const double t2 = rw[r];
+          const double PAd = dir == 0 ? Px - Ax : (dir == 1 ? Py - Ay : Pz - Az);
+          const double QCd = dir == 0 ? Qx - Cx : (dir == 1 ? Qy - Cy : Qz - Cz);
+          const double PQd = dir == 0 ? PQx : (dir == 1 ? PQy : PQz);
+          const double ABd = dir == 0 ? ABx : (dir == 1 ? ABy : ABz);
+          const double CDd = dir == 0 ? CDx : (dir == 1 ? CDy : CDz);
+          const double t2r = t2 * rho;
+          const double c00 = PAd - t2r / zeta * PQd;
+          const double d00 = QCd + t2r / eta * PQd;
+          const double b10 = 0.5 / zeta * (1.0 - t2r / zeta);
+          const double b01 = 0.5 / eta * (1.0 - t2r / eta);
+          const double b00 = 0.5 * t2 * abinv;
+          double* S1 = qs + (size_t)task * GSTR;   // [n][m], m fastest
+          double* S2 = S1 + G1;                    // [n][c][d]
+          double* S3 = S2 + G2;                    // [a][b][c][d]
+          // VRR (int_rys.F90:529-617 restated on centres A and C)
+          S1[0] = dir == 0 ? rw[R + r] * pref : 1.0;
+          if (NMAX > 1) S1[MMAX] = c00 * S1[0];
+          for (int n = 1; n < NMAX - 1; ++n) S1[(n + 1) * MMAX] = c00 * S1[n * MMAX] + n * b10 * S1[(n - 1) * MMAX];
+          for (int m = 0; m < MMAX - 1; ++m) {
+            double v0 = d00 * S1[m];
+            if (m > 0) v0 += m * b01 * S1[m - 1];
+            S1[m + 1] = v0;
+            for (int n = 1; n < NMAX; ++n) {
+              double v = d00 * S1[n * MMAX + m] + n * b00 * S1[(n - 1) * MMAX + m];
+              if (m > 0) v += m * b01 * S1[n * MMAX + m - 1];
+              S1[n * MMAX + m + 1] = v;
+            }
+          }
+          // ket HRR: (c, d+1) = (c+1, d) + (C-D)(c, d)     (int_rys.F90:636-648)
+          for (int n = 0; n < NMAX; ++n) {
+            double* w = S1 + n * MMAX;
+            for (int c = 0; c <= LC; ++c) S2[(n * (LC + 1) + c) * (LD + 1)] = w[c];
+            for (int d = 1; d <= LD; ++d) {
+              for (int c = 0; c < MMAX - d; ++c) w[c] = w[c + 1] + CDd * w[c];
+              for (int c = 0; c <= LC; ++c) S2[(n * (LC + 1) + c) * (LD + 1) + d] = w[c];
+            }
+          }
+          // bra HRR: (a, b+1) = (a+1, b) + (A-B)(a, b)     (int_rys.F90:650-660)
+          for (int k = 0; k < NKL1; ++k) {
+            for (int a = 0; a <= LA; ++a) S3[(a * (LB + 1)) * NKL1 + k] = S2[a * NKL1 + k];
+            for (int b = 1; b <= LB; ++b) {
+              for (int n = 0; n < NMAX - b; ++n) S2[n * NKL1 + k] = S2[(n + 1) * NKL1 + k] + ABd * S2[n * NKL1 + k];
+              for (int a = 0; a <= LA; ++a) S3[(a * (LB + 1) + b) * NKL1 + k] = S2[a * NKL1 + k];
+            }
+          }
+        }
+      }
+      __syncthreads();
+      // ---- B3: assembly  I(ab|cd) += sum_r gx gy gz      (int_rys.F90:677-713)
+      if (keep) {
+        any = true;
+        if (t == 0) ++st_prim;
+        for (int r = 0; r < R; ++r) {
+          const double* gx = qs + (size_t)(3 * r + 0) * GSTR + G1 + G2 + obx;
+          const double* gy = qs + (size_t)(3 * r + 1) * GSTR + G1 + G2 + oby;
+          const double* gz = qs + (size_t)(3 * r + 2) * GSTR + G1 + G2 + obz;
+          double X_[NKL1], Y_[NKL1], Z_[NKL1];
+#pragma unroll
+          for (int k = 0; k < NKL1; ++k) { X_[k] = gx[k]; Y_[k] = gy[k]; Z_[k] = gz[k]; }
+          auto body = [&](auto S) {
+            constexpr int s0 = decltype(S)::value * TKC;
+            static_for<0, Cfg::NACC>([&](auto I) {
+              constexpr int k = decltype(I)::value;
+              constexpr int ic = s0 + k / ND, id = k % ND;
+              if constexpr (ic < NC) {
+                constexpr int ix = Cart<LC>::x(ic) * (LD + 1) + Cart<LD>::x(id);
+                constexpr int iy = Cart<LC>::y(ic) * (LD + 1) + Cart<LD>::y(id);
+                constexpr int iz = Cart<LC>::z(ic) * (LD + 1) + Cart<LD>::z(id);
+                acc[k] = fma(X_[ix] * Y_[iy], Z_[iz], acc[k]);
+              }
+            });
+          };
+          if constexpr (KS == 1) body(std::integral_constant<int, 0>{});
+          else if constexpr (KS == 2) { if (slice == 0) body(std::integral_constant<int, 0>{}); else body(std::integral_constant<int, 1>{}); }
+          else { if (slice == 0) body(std::integral_constant<int, 0>{}); else if (slice == 1) body(std::integral_constant<int, 1>{}); else body(std::integral_constant<int, 2>{}); }
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- block to shared memory (Cartesian, raw), region 0
+    if (valid) {
+      if (any && t == 0) qi.nonzero = 1;  // `any` is uniform over the team
+      double* blk0 = qs;
+#pragma unroll
+      for (int k = 0; k < Cfg::NACC; ++k) {
+        int ic = slice * TKC + k / ND, id = k % ND;
+        if (ic < NC) blk0[((size_t)(ia * NB + ib) * NC + ic) * ND + id] = acc[k];
+      }
+    }
+    __syncthreads();
+    if (!(valid && qi.nonzero)) {
+      if (valid && A.mode == MODE_SCHWARZ && t == 0) A.qout[qi.bra_id] = 0.0;
+      if (valid && A.mode == MODE_BLOCK) {
+        for (int e = t; e < PT[0].nout * PT[1].nout * PT[2].nout * PT[3].nout; e += TS) A.blockout[e] = 0.0;
+      }
+      // all teams still take part in the barriers below
+    }
+    // ---- normalisation + pure projection, index by index (int2.F90:1187-1207; int_rys.F90:715-785)
+    // dims (a,b,c,d) -> transform d, c, b, a ; ping-pong between region 0 and region 1
+    double* src = qs;
+    double* dst = qs + Cfg::NCART4;
+    int n0 = NA, n1 = NB, n2 = NC, n3 = ND;
+    const bool work = valid && qi.nonzero;
+    if (LD >= 2) {
+      if (work) proj_pass(src, dst, n0 * n1 * n2, n3, 1, PT[3], t, TS);
+      n3 = PT[3].nout;
+      double* tmp = src; src = dst; dst = tmp;
+      __syncthreads();
+    }
+    if (LC >= 2) {
+      if (work) proj_pass(src, dst, n0 * n1, n2, n3, PT[2], t, TS);
+      n2 = PT[2].nout;
+      double* tmp = src; src = dst; dst = tmp;
+      __syncthreads();
+    }
+    if (LB >= 2) {
+      if (work) proj_pass(src, dst, n0, n1, n2 * n3, PT[1], t, TS);
+      n1 = PT[1].nout;
+      double* tmp = src; src = dst; dst = tmp;
+      __syncthreads();
+    }
+    if (LA >= 2) {
+      if (work) proj_pass(src, dst, 1, n0, n1 * n2 * n3, PT[0], t, TS);
+      n0 = PT[0].nout;
+      double* tmp = src; src = dst; dst = tmp;
+      __syncthreads();
+    }
+    const int ntot = n0 * n1 * n2 * n3;
+    if (A.mode == MODE_SCHWARZ) {
+      // Q = sqrt(max |(ij|ij)|), int2.F90:1727-1728
+      if (work) {
+        double mx = 0.0;
+        for (int e = t; e < ntot; e += TS) mx = fmax(mx, fabs(src[e]));
+        dst[t] = mx;
+      }
+      __syncthreads();
+      if (work && t == 0) {
+        double mx = 0.0;
+        for (int k = 0; k < TS && k < ntot; ++k) mx = fmax(mx, dst[k]);
+        A.qout[qi.bra_id] = sqrt(mx);
+      }
+      continue;
+    }
+    if (A.mode == MODE_BLOCK) {
+      if (work) for (int e = t; e < ntot; e += TS) A.blockout[e] = src[e];
+      continue;
+    }
+    // ---- element cutoff (int2.F90:1806-1812) and shell-level coincidence factor (int2.F90:1849-1851)
+    if (work) {
+      const double fac = (double)qi.fac, cut = A.cutoff;
+      unsigned nz = 0;
+      for (int e = t; e < ntot; e += TS) {
+        double v = src[e];
+        bool z = fabs(v) < cut;
+        nz += !z;
+        src[e] = z ? 0.0 : v * fac;
+      }
+      st_ints += (unsigned long long)nz * (unsigned)(8.0f * qi.fac);
+    }
+    __syncthreads();
+    if (work) {
+      if (A.mode == MODE_SYM) digest_sym(A, src, n0, n1, n2, n3, qi.oa, qi.ob, qi.oc, qi.od, t, TS);
+      else digest_gen(A, src, n0, n1, n2, n3, qi.oa, qi.ob, qi.oc, qi.od, t, TS);
+    }
+  }
+  if (A.stat) {
+    if (st_prim) atomicAdd(A.stat, st_prim);
+    if (st_ints) atomicAdd(A.stat + 1, st_ints);
+  }
+}
+
+template <int LA, int LB, int LC, int LD>
+cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
+  using Cfg = ClassCfg<LA, LB, LC, LD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(eri_kernel<LA, LB, LC, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  eri_kernel<LA, LB, LC, LD><<<nblocks, Cfg::NT, Cfg::SMEM, st>>>(args);
+  return cudaGetLastError();
+}
+
+template <int LA, int LB, int LC, int LD>
+int class_qpb() { return ClassCfg<LA, LB, LC, LD>::QPB; }
+
+using LaunchFn = cudaError_t (*)(const EriArgs&, int, cudaStream_t);
+struct ClassEntry { LaunchFn launch; int qpb; int nt; size_t smem; };
+
+}  // namespace oqpb

@@ -1,0 +1,1286 @@
+// libopenqp_b200: host side of the C ABI (include/oqp_b200.h) and the small device kernels around the
+// ERI/digestion kernel family (eri_kernel.cuh): pair table, Schwarz, shell densities, quartet enumeration.
+//
+// Reference map (what each piece replaces):
+//   k_pair_count / k_pair_fill   int2_pair_storage%alloc / int2_prepare_pair     int2_pairs.F90:74-266
+//   schwarz()                    ints_exchange                                    int2.F90:1582-1737
+//   k_shlden_*                   shlden / shltd / shell_den_screen_mrsf           int2.F90:999-1047, tdhf_lib.F90:300-325,
+//                                                                                  tdhf_mrsf_lib.F90:189-214
+//   k_enum                       the i,j,k,l loops + screen_ij / screen_ijkl      int2.F90:756-805, 963-986
+//   run_build()                  int2_twoei                                       int2.F90:589-923
+//   k_fock_post                  fock_jk post-scaling                             scf_addons.F90:1177-1185
+// There is no CPU fallback: every compute entry needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/oqp_b200.h"
+#include "eri_kernel.cuh"
+#include "pure_tables.inc"
+#include "rys_tables.inc"
+
+using namespace oqpb;
+
+namespace oqpb {
+const ClassEntry* class_table();  // eri_inst_*.cu, indexed by quartet class
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      char buf_[512];                                                                              \
+      snprintf(buf_, sizeof buf_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      ctx->err = buf_;                                                                             \
+      return OQPB_ERR_CUDA;                                                                        \
+    }                                                                                              \
+  } while (0)
+
+namespace {
+
+constexpr int NPC = 10;  // pair classes ss ps pp ds dp dd fs fp fd ff
+inline int pair_class(int la, int lb) { return la * (la + 1) / 2 + lb; }
+inline int quartet_class(int pa, int pb) { return pa * (pa + 1) / 2 + pb; }
+const int PC_LA[NPC] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3};
+const int PC_LB[NPC] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3};
+
+struct Cutoffs {
+  double integral, pair, quartet, exponent;
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t b) {
+    if (b <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, b);
+    if (e == cudaSuccess) bytes = b;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const { return (T*)p; }
+};
+
+struct PairTable {
+  // entries grouped by pair class; within a class sorted by Q descending once Schwarz is known
+  std::vector<PairEntry> ent;
+  std::vector<int> canon;  // canonical pair id tri(i,j), i>=j by shell index
+  std::vector<double> Q;
+  int cls_off[NPC + 1] = {0};
+  DevBuf d_ent, d_prim, d_Q, d_canon;
+  long nprim = 0;
+};
+
+// FLOP model of SURVEY.md 8(d-1) (restates int_rys.F90:406, 471-713)
+double fprim_model(int l1, int l2, int l3, int l4) {
+  int a[4] = {l1, l2, l3, l4};
+  if (a[0] > a[1]) std::swap(a[0], a[1]);
+  if (a[2] > a[3]) std::swap(a[2], a[3]);
+  if (a[0] + a[1] > a[2] + a[3]) { std::swap(a[0], a[2]); std::swap(a[1], a[3]); }
+  l1 = a[0]; l2 = a[1]; l3 = a[2]; l4 = a[3];
+  int R = (l1 + l2 + l3 + l4) / 2 + 1, n = l1 + l2 + 1, m = l3 + l4 + 1;
+  int coef = 15 + (m > 1 ? 6 : 0) + (n > 1 ? 6 : 0), vrr = 0;
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < m; j++) {
+      if (i + j == 0) continue;
+      else if (i + j == 1) vrr += 1;
+      else if (i == 1 && j == 1) vrr += 3;
+      else if (i < 2 || j < 2) vrr += 4;
+      else vrr += 7;
+    }
+  int hrr = 0;
+  for (int k = 1; k <= l3; k++) hrr += 2 * n * (m - k);
+  for (int i = 1; i <= l1; i++) hrr += 2 * (l3 + 1) * (l4 + 1) * (n - i);
+  int N = ncart(l1) * ncart(l2) * ncart(l3) * ncart(l4);
+  return 40.0 * R + R * (double)(coef + 3 * vrr + 3 * hrr + 3 * N);
+}
+
+}  // namespace
+
+struct oqpb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  // basis (host copy)
+  int nshell = 0, nprim = 0, nbf = 0, harmonic_active = 0, lmax = 0;
+  std::vector<int> am, harm, ncontr, goff, aooff, naos;
+  std::vector<double> ex, cc, cen;
+  int pure_l[4] = {0, 0, 0, 0};
+  bool have_basis = false, have_cutoff = false, have_screen = false;
+  // device basis
+  DevBuf d_am, d_ncontr, d_goff, d_aooff, d_naos, d_ex, d_cc, d_xyz;
+  DevBuf d_rys, d_proj;  // Rys tables, 4 x ProjTable (per l, for the ctx's pure flags)
+  double cutoff = 5e-11;
+  Cutoffs cut{};
+  PairTable run;
+  std::vector<double> Qmat;  // nshell x nshell (host)
+  DevBuf d_Qmat, d_dsh, d_maxden, d_ok, d_d4, d_rowsbuf;
+  // work
+  DevBuf d_tasks, d_counters, d_Dsq, d_F, d_Din, d_stats, d_gen_in, d_gen_out;
+  size_t task_cap = (size_t)1 << 23;
+  int rank = 0, nranks = 1;
+  // stats of the last build
+  long long st_survivors = 0, st_skipped = 0, st_launches = 0;
+  double st_flops = 0, st_kernel_ms = 0;
+  bool record = false;
+  std::vector<int> rec;  // recorded shell quadruples
+  unsigned* h_counts = nullptr;  // pinned
+  size_t h_counts_cap = 0;
+  double fp64_peak = 0;
+};
+
+// ===================================================================================== device kernels
+namespace {
+
+__device__ __forceinline__ void pair_from_index(long id, int& i, int& j) {
+  // id = i(i+1)/2 + j, j <= i
+  i = (int)((sqrt(8.0 * (double)id + 1.0) - 1.0) * 0.5);
+  while ((long)i * (i + 1) / 2 > id) --i;
+  while ((long)(i + 1) * (i + 2) / 2 <= id) ++i;
+  j = (int)(id - (long)i * (i + 1) / 2);
+}
+
+// int2_pairs.F90:179-266: predicate of the fill pass; order: lower-AM shell's primitives outermost
+template <bool FILL>
+__global__ void k_pairs(int nshell, long npairs, const int* __restrict__ am, const int* __restrict__ ncontr,
+                        const int* __restrict__ goff, const double* __restrict__ ex, const double* __restrict__ cc,
+                        const double* __restrict__ xyz, double exponent_cutoff, double quartet_cutoff,
+                        int* __restrict__ cnt, const PairEntry* __restrict__ ent, double* __restrict__ prim, long nent) {
+  long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  int i, j, poff = 0;
+  if (FILL) {
+    if (id >= nent) return;
+    i = ent[id].sa;
+    j = ent[id].sb;
+    poff = ent[id].poff;
+    if (ent[id].pcnt == 0) return;
+  } else {
+    if (id >= npairs) return;
+    pair_from_index(id, i, j);
+  }
+  int sha = i, shb = j;  // reference order: lower AM first (int2_pairs.F90:202-212); equal AM: (i, j)
+  if (FILL) {
+    // entries store the higher-AM shell first; the reference's outer loop is the lower-AM shell
+    if (am[i] > am[j]) { sha = j; shb = i; }
+  } else {
+    if (am[i] > am[j]) { sha = j; shb = i; }
+  }
+  const double ax = xyz[3 * sha], ay = xyz[3 * sha + 1], az = xyz[3 * sha + 2];
+  const double bx = xyz[3 * shb], by = xyz[3 * shb + 1], bz = xyz[3 * shb + 2];
+  const double ab2 = (ax - bx) * (ax - bx) + (ay - by) * (ay - by) + (az - bz) * (az - bz);
+  const double sqrtpito52 = 5.914967172795612486;  // sqrt(2) * pi^(5/4)
+  int n = 0;
+  for (int p1 = 0; p1 < ncontr[sha]; ++p1)
+    for (int p2 = 0; p2 < ncontr[shb]; ++p2) {
+      double a1 = ex[goff[sha] + p1], a2 = ex[goff[shb] + p2];
+      double gam = a1 + a2;
+      double e12 = a1 * a2 * ab2;
+      if (e12 > gam * exponent_cutoff) continue;
+      double gi = 1.0 / gam;
+      e12 = e12 * gi;
+      double k1 = cc[goff[sha] + p1] * cc[goff[shb] + p2] * exp(-e12);
+      if (fabs(k1) < quartet_cutoff) continue;
+      if (FILL) {
+        double* o = prim + (size_t)(poff + n) * PRIM_STRIDE;
+        o[0] = (a1 * ax + a2 * bx) * gi;
+        o[1] = (a1 * ay + a2 * by) * gi;
+        o[2] = (a1 * az + a2 * bz) * gi;
+        o[3] = gam;
+        o[4] = sqrtpito52 * k1;
+      }
+      ++n;
+    }
+  if (!FILL) cnt[id] = n;
+}
+
+__global__ void k_expand_packed(const double* __restrict__ dp, double* __restrict__ dsq, int nbf) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long)nbf * nbf) return;
+  int a = (int)(e / nbf), b = (int)(e % nbf);
+  dsq[e] = dp[tri_idx(a, b)];
+}
+__global__ void k_add(const double* a, const double* b, double* c, long n) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) c[e] = a[e] + b[e];
+}
+
+// shlden int2.F90:999-1047 (packed densities, all focks)
+__global__ void k_shlden_packed(int nshell, long npairs, const int* __restrict__ aooff, const int* __restrict__ naos,
+                                const double* __restrict__ d, int nfocks, long ntri, double* __restrict__ dsh,
+                                unsigned long long* maxden) {
+  long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= npairs) return;
+  int si, sj;
+  pair_from_index(id, si, sj);
+  int mini = aooff[si], maxi = mini + naos[si] - 1, minj = aooff[sj], maxj0 = minj + naos[sj] - 1;
+  double dmax = 0.0;
+  for (int f = 0; f < nfocks; ++f)
+    for (int i = mini; i <= maxi; ++i) {
+      int maxj = (si == sj) ? i : maxj0;
+      for (int j = minj; j <= maxj; ++j) dmax = fmax(dmax, fabs(d[(size_t)f * ntri + tri_idx(i, j)]));
+    }
+  dsh[(size_t)si * nshell + sj] = dmax;
+  dsh[(size_t)sj * nshell + si] = dmax;
+  atomicMax(maxden, (unsigned long long)__double_as_longlong(dmax));
+}
+// shltd / shell_den_screen_mrsf: dsh(I,J) (I>=J) = max |X(m, mu in J, nu in I)| over the interleaved
+// layout X[(nu*nbf + mu)*NM + m]
+__global__ void k_shlden_gen(int nshell, long npairs, const int* __restrict__ aooff, const int* __restrict__ naos,
+                             const double* __restrict__ X, int NM, int nbf, double* __restrict__ dsh,
+                             unsigned long long* maxden) {
+  long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= npairs) return;
+  int si, sj;
+  pair_from_index(id, si, sj);
+  double dmax = 0.0;
+  for (int nu = aooff[si]; nu < aooff[si] + naos[si]; ++nu)
+    for (int mu = aooff[sj]; mu < aooff[sj] + naos[sj]; ++mu) {
+      const double* p = X + ((size_t)nu * nbf + mu) * NM;
+      for (int m = 0; m < NM; ++m) dmax = fmax(dmax, fabs(p[m]));
+    }
+  dsh[(size_t)si * nshell + sj] = dmax;
+  dsh[(size_t)sj * nshell + si] = dmax;
+  atomicMax(maxden, (unsigned long long)__double_as_longlong(dmax));
+}
+
+// per-entry build data: ok = bra-level test passes (screen_ij, int2.F90:763-772); d4 = 4*dsh(sa,sb)
+__global__ void k_entry_screen(long nent, const PairEntry* __restrict__ ent, const double* __restrict__ Q,
+                               const double* __restrict__ dsh, int nshell, const unsigned long long* maxden,
+                               double cutoff, int* __restrict__ ok, double* __restrict__ d4) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nent) return;
+  double md = __longlong_as_double((long long)*maxden);
+  ok[e] = !(__dmul_rn(Q[e], md) < cutoff);
+  d4[e] = 4.0 * dsh[(size_t)ent[e].sa * nshell + ent[e].sb];
+}
+
+// Quartet enumeration for one (bra class, ket class) chunk: CTA per bra entry, threads over ket entries.
+// Predicate = screen_ijkl, int2.F90:975-986, evaluated in the reference's operation order without FMA.
+// Lists are Q-descending, so kets beyond kmax[bra] cannot survive (bound with 4*max_den) and are not visited.
+__global__ void k_enum(const PairEntry* __restrict__ bra, const PairEntry* __restrict__ ket,
+                       const double* __restrict__ Qb, const double* __restrict__ Qk, const double* __restrict__ d4b,
+                       const double* __restrict__ d4k, const int* __restrict__ okb, const int* __restrict__ okk,
+                       const int* __restrict__ canb, const int* __restrict__ cank, const int* __restrict__ kmax,
+                       int p0, int p1, int pstride, int diag, const double* __restrict__ dsh, int nshell, double cutoff,
+                       int2* __restrict__ tasks, unsigned* __restrict__ count, unsigned cap, int use_smem) {
+  extern __shared__ double rows[];
+  int p = p0 + blockIdx.x * pstride;
+  if (p >= p1) return;
+  const PairEntry eb = bra[p];
+  const int nk = diag ? min(kmax[p], p + 1) : kmax[p];
+  if (nk <= 0) return;
+  const double* rowa = dsh + (size_t)eb.sa * nshell;
+  const double* rowb = dsh + (size_t)eb.sb * nshell;
+  if (use_smem) {
+    for (int s = threadIdx.x; s < nshell; s += blockDim.x) {
+      rows[s] = rowa[s];
+      rows[nshell + s] = rowb[s];
+    }
+    __syncthreads();
+    rowa = rows;
+    rowb = rows + nshell;
+  }
+  const double qb = Qb[p], db4 = d4b[p];
+  const int okp = okb[p], canp = canb[p];
+  for (int q0 = 0; q0 < nk; q0 += blockDim.x) {
+    int q = q0 + threadIdx.x;
+    bool surv = false;
+    if (q < nk) {
+      const PairEntry ek = ket[q];
+      double m = fmax(fmax(fmax(db4, d4k[q]), fmax(rowb[ek.sb], rowb[ek.sa])), fmax(rowa[ek.sb], rowa[ek.sa]));
+      double res = __dmul_rn(__dmul_rn(qb, Qk[q]), m);
+      int bra_ok = (canp >= cank[q]) ? okp : okk[q];  // the canonically larger pair is the reference's bra
+      surv = bra_ok && !(res < cutoff);
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, surv);
+    if (mask) {
+      int lane = threadIdx.x & 31;
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(count, (unsigned)__popc(mask));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (surv) {
+        unsigned pos = base + __popc(mask & ((1u << lane) - 1));
+        if (pos < cap) tasks[pos] = make_int2(p, q);
+      }
+    }
+  }
+}
+
+__global__ void k_fock_post(double* f, int nbf, long ntri, int nfocks) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ntri * nfocks) return;
+  long t = e % ntri;
+  int i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while ((long)i * (i + 1) / 2 > t) --i;
+  while ((long)(i + 1) * (i + 2) / 2 <= t) ++i;
+  long j = t - (long)i * (i + 1) / 2;
+  double v = 0.5 * f[e];
+  if (j == i) v *= 2.0;
+  f[e] = v;
+}
+
+// TD helpers: d2(mu,nu,v) column-major -> interleaved X[(nu*nbf+mu)*NM + m] with m = v (+ nvec for the
+// antisymmetric copy):  comp 0: P + P^T, comp 1: P - P^T   (see oqpb_jk_td)
+__global__ void k_td_pack(const double* __restrict__ d2, double* __restrict__ X, int nbf, int nvec, int ncomp, int mode) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long n2 = (long)nbf * nbf;
+  if (e >= n2 * nvec) return;
+  int v = (int)(e / n2);
+  long r = e % n2;
+  int nu = (int)(r / nbf), mu = (int)(r % nbf);
+  double p = d2[e], pt = d2[(size_t)v * n2 + (size_t)mu * nbf + nu];
+  int NM = nvec * ncomp;
+  if (mode == 0) {  // plain (TDA)
+    X[(size_t)r * NM + v] = p;
+  } else {
+    X[(size_t)r * NM + v] = p + pt;
+    if (ncomp > 1) X[(size_t)r * NM + nvec + v] = p - pt;
+  }
+}
+__global__ void k_td_unpack(const double* __restrict__ X, double* __restrict__ out, int nbf, int nvec, int NM, int comp) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long n2 = (long)nbf * nbf;
+  if (e >= n2 * nvec) return;
+  int v = (int)(e / n2);
+  long r = e % n2;
+  out[e] = X[(size_t)r * NM + comp * nvec + v];
+}
+
+__global__ void k_rys_test(EriArgs A, int nroots, int npts, const double* x, double* t2, double* w) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npts) return;
+  for (int f = 0; f < 2 * nroots; ++f) {
+    double v = 0;
+    switch (nroots) {
+      case 1: v = rys_eval<1>(A, x[i], f); break;
+      case 2: v = rys_eval<2>(A, x[i], f); break;
+      case 3: v = rys_eval<3>(A, x[i], f); break;
+      case 4: v = rys_eval<4>(A, x[i], f); break;
+      case 5: v = rys_eval<5>(A, x[i], f); break;
+      case 6: v = rys_eval<6>(A, x[i], f); break;
+      case 7: v = rys_eval<7>(A, x[i], f); break;
+    }
+    if (f < nroots) t2[(size_t)i * nroots + f] = v;
+    else w[(size_t)i * nroots + f - nroots] = v;
+  }
+}
+
+__global__ void k_fp64_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace
+
+// ===================================================================================== host helpers
+namespace {
+
+template <class T>
+int upload(oqpb_ctx* ctx, DevBuf& b, const std::vector<T>& v) {
+  CK(b.ensure(std::max<size_t>(v.size(), 1) * sizeof(T)));
+  if (!v.empty()) CK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return OQPB_OK;
+}
+
+// projection table for shell type l: rows = reference output order (pure CCA order or reference Cartesian
+// order), columns = my internal Cartesian order; unit normalisation (shells_pnrm2, constants.F90:121-164) folded in
+void build_proj(int l, int pure, ProjTable& T) {
+  static const int RX[4][10] = {{0}, {1, 0, 0}, {2, 0, 0, 1, 1, 0}, {3, 0, 0, 2, 2, 1, 0, 1, 0, 1}};
+  static const int RY[4][10] = {{0}, {0, 1, 0}, {0, 2, 0, 1, 0, 1}, {0, 3, 0, 1, 0, 2, 2, 0, 1, 1}};
+  memset(&T, 0, sizeof T);
+  int nc = ncart(l);
+  auto my_index = [&](int x, int y) {
+    int k = 0;
+    for (int xx = l; xx >= 0; --xx)
+      for (int yy = l - xx; yy >= 0; --yy) {
+        if (xx == x && yy == y) return k;
+        ++k;
+      }
+    return -1;
+  };
+  auto df = [](int n) { double r = 1; for (int k = n; k > 1; k -= 2) r *= k; return r; };
+  T.nout = (pure && l >= 2) ? 2 * l + 1 : nc;
+  for (int rc = 0; rc < nc; ++rc) {  // reference Cartesian component rc
+    int x = RX[l][rc], y = RY[l][rc], z = l - x - y;
+    double pn = std::sqrt(df(2 * l - 1) / (df(2 * x - 1) * df(2 * y - 1) * df(2 * z - 1)));
+    int mi = my_index(x, y);
+    if (pure && l >= 2) {
+      for (int t = 0; t < PURE_NTERM_H[l - 2][rc]; ++t) {
+        int o = PURE_OUT_H[l - 2][rc][t];
+        int k = T.nterm[o]++;
+        T.idx[o][k] = mi;
+        T.coef[o][k] = PURE_COEF_H[l - 2][rc][t] * pn;
+      }
+    } else {
+      T.nterm[rc] = 1;
+      T.idx[rc][0] = mi;
+      T.coef[rc][0] = pn;
+    }
+  }
+}
+
+int free_pairtable(PairTable& t) {
+  t.d_ent.release(); t.d_prim.release(); t.d_Q.release(); t.d_canon.release();
+  t.ent.clear(); t.canon.clear(); t.Q.clear();
+  return 0;
+}
+
+// Build a pair table for the given cutoffs.  Entries: every shell pair i>=j (zero-primitive pairs kept so the
+// quartet bookkeeping -- nschwz -- matches the reference's loops exactly), grouped by pair class.
+int build_pairtable(oqpb_ctx* ctx, const Cutoffs& c, PairTable& T, const std::vector<double>* Qmat) {
+  const int ns = ctx->nshell;
+  const long npairs = (long)ns * (ns + 1) / 2;
+  DevBuf d_cnt;
+  CK(d_cnt.ensure(npairs * sizeof(int)));
+  int thr = 128;
+  k_pairs<false><<<(unsigned)((npairs + thr - 1) / thr), thr, 0, ctx->stream>>>(
+      ns, npairs, ctx->d_am.as<int>(), ctx->d_ncontr.as<int>(), ctx->d_goff.as<int>(), ctx->d_ex.as<double>(),
+      ctx->d_cc.as<double>(), ctx->d_xyz.as<double>(), c.exponent, c.quartet, d_cnt.as<int>(), nullptr, nullptr, 0);
+  CK(cudaGetLastError());
+  std::vector<int> cnt(npairs);
+  CK(cudaMemcpyAsync(cnt.data(), d_cnt.p, npairs * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  d_cnt.release();
+  // group by class
+  std::vector<std::vector<int>> bycls(NPC);
+  {
+    long id = 0;
+    for (int i = 0; i < ns; ++i)
+      for (int j = 0; j <= i; ++j, ++id) {
+        int la = ctx->am[i], lb = ctx->am[j];
+        int pc = la >= lb ? pair_class(la, lb) : pair_class(lb, la);
+        bycls[pc].push_back((int)id);
+      }
+  }
+  if (Qmat) {
+    for (int pc = 0; pc < NPC; ++pc) {
+      auto& v = bycls[pc];
+      auto qof = [&](int id) {
+        int i = (int)((std::sqrt(8.0 * id + 1.0) - 1.0) * 0.5);
+        while ((long)i * (i + 1) / 2 > id) --i;
+        while ((long)(i + 1) * (i + 2) / 2 <= id) ++i;
+        int j = id - i * (i + 1) / 2;
+        return (*Qmat)[(size_t)i * ns + j];
+      };
+      std::vector<std::pair<double, int>> key(v.size());
+      for (size_t k = 0; k < v.size(); ++k) key[k] = {-qof(v[k]), v[k]};
+      std::sort(key.begin(), key.end());
+      for (size_t k = 0; k < v.size(); ++k) v[k] = key[k].second;
+    }
+  }
+  T.ent.clear(); T.canon.clear(); T.Q.clear();
+  long poff = 0;
+  for (int pc = 0; pc < NPC; ++pc) {
+    T.cls_off[pc] = (int)T.ent.size();
+    for (int id : bycls[pc]) {
+      int i = (int)((std::sqrt(8.0 * id + 1.0) - 1.0) * 0.5);
+      while ((long)i * (i + 1) / 2 > id) --i;
+      while ((long)(i + 1) * (i + 2) / 2 <= id) ++i;
+      int j = id - i * (i + 1) / 2;
+      PairEntry e;
+      if (ctx->am[i] >= ctx->am[j]) { e.sa = i; e.sb = j; } else { e.sa = j; e.sb = i; }
+      e.poff = (int)poff;
+      e.pcnt = cnt[id];
+      poff += cnt[id];
+      T.ent.push_back(e);
+      T.canon.push_back(id);
+      T.Q.push_back(Qmat ? (*Qmat)[(size_t)i * ns + j] : 0.0);
+    }
+  }
+  T.cls_off[NPC] = (int)T.ent.size();
+  T.nprim = poff;
+  if (poff > 2000000000L) { ctx->err = "pair table too large"; return OQPB_ERR_UNSUPPORTED; }
+  int rc;
+  if ((rc = upload(ctx, T.d_ent, T.ent))) return rc;
+  if ((rc = upload(ctx, T.d_canon, T.canon))) return rc;
+  if ((rc = upload(ctx, T.d_Q, T.Q))) return rc;
+  CK(T.d_prim.ensure(std::max<size_t>(poff, 1) * PRIM_STRIDE * sizeof(double)));
+  long nent = (long)T.ent.size();
+  k_pairs<true><<<(unsigned)((nent + thr - 1) / thr), thr, 0, ctx->stream>>>(
+      ns, npairs, ctx->d_am.as<int>(), ctx->d_ncontr.as<int>(), ctx->d_goff.as<int>(), ctx->d_ex.as<double>(),
+      ctx->d_cc.as<double>(), ctx->d_xyz.as<double>(), c.exponent, c.quartet, nullptr, T.d_ent.as<PairEntry>(),
+      T.d_prim.as<double>(), nent);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return OQPB_OK;
+}
+
+void fill_common_args(oqpb_ctx* ctx, const PairTable& T, int pca, int pcb, EriArgs& A) {
+  memset(&A, 0, sizeof A);
+  A.bra = T.d_ent.as<PairEntry>() + T.cls_off[pca];
+  A.ket = T.d_ent.as<PairEntry>() + T.cls_off[pcb];
+  A.prim = T.d_prim.as<double>();
+  A.xyz = ctx->d_xyz.as<double>();
+  A.aooff = ctx->d_aooff.as<int>();
+  int R = (PC_LA[pca] + PC_LB[pca] + PC_LA[pcb] + PC_LB[pcb]) / 2 + 1;
+  A.rys_tab = ctx->d_rys.as<double>() + RYS_OFF_H[R - 1];
+  A.rys_xmax = RYS_XMAX_H[R - 1];
+  for (int k = 0; k < 7; ++k) { A.herm_r[k] = RYS_HERM_R_H[R - 1][k]; A.herm_w[k] = RYS_HERM_W_H[R - 1][k]; }
+  A.nbf = ctx->nbf;
+  // projection tables for (la, lb, lc, ld): device array of 4 ProjTables per quartet class is assembled on the fly
+}
+
+// device array with the 4 projection tables of a quartet class (index = l, ctx-wide pure flag per l)
+const ProjTable* proj_for(oqpb_ctx* ctx, int pca, int pcb) {
+  // d_proj holds 55 x 4 tables
+  return ctx->d_proj.as<ProjTable>() + (size_t)quartet_class(pca, pcb) * 4;
+}
+
+int ensure_counts(oqpb_ctx* ctx, size_t n) {
+  if (n <= ctx->h_counts_cap) return OQPB_OK;
+  if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  ctx->h_counts = nullptr;
+  size_t cap = std::max<size_t>(n * 2, 4096);
+  CK(cudaMallocHost((void**)&ctx->h_counts, cap * sizeof(unsigned)));
+  ctx->h_counts_cap = cap;
+  return OQPB_OK;
+}
+
+// Schwarz matrix on the device: ints_exchange, int2.F90:1582-1737
+int schwarz(oqpb_ctx* ctx) {
+  Cutoffs c{1.0e-15, 1.0e-17, 1.0e-17, 50.0};  // int2.F90:1600-1604
+  PairTable T;
+  int rc = build_pairtable(ctx, c, T, nullptr);
+  if (rc) return rc;
+  const int ns = ctx->nshell;
+  size_t nent = T.ent.size();
+  DevBuf d_q, d_tasks, d_cnt;
+  CK(d_q.ensure(nent * sizeof(double)));
+  CK(cudaMemsetAsync(d_q.p, 0, nent * sizeof(double), ctx->stream));
+  CK(d_cnt.ensure(2 * NPC * sizeof(unsigned)));
+  std::vector<unsigned> hc(2 * NPC, 0);
+  const ClassEntry* tab = class_table();
+  for (int pc = 0; pc < NPC; ++pc) {
+    int n = T.cls_off[pc + 1] - T.cls_off[pc];
+    hc[2 * pc] = n;
+    hc[2 * pc + 1] = 0;
+  }
+  CK(cudaMemcpyAsync(d_cnt.p, hc.data(), hc.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+  for (int pc = 0; pc < NPC; ++pc) {
+    int n = T.cls_off[pc + 1] - T.cls_off[pc];
+    if (n == 0) continue;
+    if (PC_LA[pc] > ctx->lmax) continue;
+    std::vector<int2> tasks(n);
+    for (int k = 0; k < n; ++k) tasks[k] = make_int2(k, k);
+    CK(d_tasks.ensure(n * sizeof(int2)));
+    CK(cudaMemcpyAsync(d_tasks.p, tasks.data(), n * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    EriArgs A;
+    fill_common_args(ctx, T, pc, pc, A);
+    A.tasks = d_tasks.as<int2>();
+    A.ntasks = d_cnt.as<unsigned>() + 2 * pc;
+    A.counter = d_cnt.as<unsigned>() + 2 * pc + 1;
+    A.prim_cutoff = c.pair * c.pair;
+    A.cutoff = 0.0;
+    A.proj = proj_for(ctx, pc, pc);
+    A.mode = MODE_SCHWARZ;
+    A.qout = d_q.as<double>() + T.cls_off[pc];
+    const ClassEntry& ce = tab[quartet_class(pc, pc)];
+    int nb = std::min((n + ce.qpb - 1) / ce.qpb, 148 * 16);
+    CK(ce.launch(A, nb, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // tasks vector lifetime
+  }
+  std::vector<double> q(nent);
+  CK(cudaMemcpyAsync(q.data(), d_q.p, nent * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->Qmat.assign((size_t)ns * ns, 0.0);
+  for (size_t e = 0; e < nent; ++e) {
+    int i = T.ent[e].sa, j = T.ent[e].sb;
+    ctx->Qmat[(size_t)i * ns + j] = ctx->Qmat[(size_t)j * ns + i] = q[e];
+  }
+  free_pairtable(T);
+  d_q.release(); d_tasks.release(); d_cnt.release();
+  return OQPB_OK;
+}
+
+struct BuildSpec {
+  int mode;            // MODE_SYM / MODE_GEN
+  // SYM
+  int nmat = 0;
+  const double* DJ[MAX_MATS];
+  const double* DK[MAX_MATS];
+  double* F[MAX_MATS];
+  // GEN
+  const double* Pgen = nullptr;
+  double* Fgen = nullptr;
+  int gen_nm = 0, gen_ncoul = 0, gen_nvec = 0;
+  double cj = 0, ck = 0;
+  double digest_flops_per_int = 0;
+};
+
+// int2_twoei (int2.F90:589-923): screening data must already be in d_dsh / d_maxden.
+int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
+  const PairTable& T = ctx->run;
+  const int ns = ctx->nshell;
+  const long nent = (long)T.ent.size();
+  const double cutoff = ctx->cut.integral;
+  CK(ctx->d_ok.ensure(nent * sizeof(int)));
+  CK(ctx->d_d4.ensure(nent * sizeof(double)));
+  k_entry_screen<<<(unsigned)((nent + 255) / 256), 256, 0, ctx->stream>>>(
+      nent, T.d_ent.as<PairEntry>(), T.d_Q.as<double>(), ctx->d_dsh.as<double>(), ns,
+      ctx->d_maxden.as<unsigned long long>(), cutoff, ctx->d_ok.as<int>(), ctx->d_d4.as<double>());
+  CK(cudaGetLastError());
+  double maxden = 0;
+  CK(cudaMemcpyAsync(&maxden, ctx->d_maxden.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const double bound4 = 4.0 * maxden;
+
+  // ---- plan: per class pair, kmax[p] by a two-pointer sweep over the Q-sorted lists, chunk boundaries
+  struct Chunk { int pca, pcb, p0, p1; size_t cand; };
+  std::vector<Chunk> chunks;
+  std::vector<int> kmax(nent, 0);  // per bra entry, for the ket class currently planned -> stored per class pair
+  std::vector<std::vector<int>> kmax_all;  // index by class pair order
+  std::vector<std::pair<int, int>> cps;
+  long long total_local = 0;
+  const int nr = ctx->nranks, rk = ctx->rank;
+  for (int pca = 0; pca < NPC; ++pca) {
+    int na = T.cls_off[pca + 1] - T.cls_off[pca];
+    if (na == 0) continue;
+    for (int pcb = 0; pcb <= pca; ++pcb) {
+      int nb = T.cls_off[pcb + 1] - T.cls_off[pcb];
+      if (nb == 0) continue;
+      const double* Qa = T.Q.data() + T.cls_off[pca];
+      const double* Qb = T.Q.data() + T.cls_off[pcb];
+      std::vector<int> km(na, 0);
+      int q = nb;  // number of kets that can survive for the current bra (monotone non-increasing in p)
+      for (int p = 0; p < na; ++p) {
+        while (q > 0 && ((Qa[p] * Qb[q - 1]) * bound4 < cutoff)) --q;
+        km[p] = q;
+      }
+      // chunking over this rank's bras (p % nranks == rank)
+      size_t cand = 0;
+      int p0 = 0;
+      bool diag = pca == pcb;
+      for (int p = 0; p < na; ++p) {
+        if (p % nr != rk) continue;
+        total_local += diag ? (p + 1) : nb;
+        size_t c = diag ? (size_t)std::min(km[p], p + 1) : (size_t)km[p];
+        if (cand + c > ctx->task_cap && cand > 0) {
+          chunks.push_back({pca, pcb, p0, p, cand});
+          p0 = p;
+          cand = 0;
+        }
+        cand += c;
+      }
+      if (cand > 0) chunks.push_back({pca, pcb, p0, na, cand});
+      kmax_all.push_back(std::move(km));
+      cps.push_back({pca, pcb});
+    }
+  }
+  // upload kmax arrays (concatenated)
+  std::vector<int> km_cat;
+  std::vector<size_t> km_off(cps.size());
+  for (size_t c = 0; c < cps.size(); ++c) {
+    km_off[c] = km_cat.size();
+    km_cat.insert(km_cat.end(), kmax_all[c].begin(), kmax_all[c].end());
+  }
+  DevBuf& d_km = ctx->d_rowsbuf;
+  int rc;
+  if ((rc = upload(ctx, d_km, km_cat))) return rc;
+  auto cp_index = [&](int pca, int pcb) {
+    for (size_t c = 0; c < cps.size(); ++c) if (cps[c].first == pca && cps[c].second == pcb) return c;
+    return (size_t)0;
+  };
+
+  size_t nch = chunks.size();
+  if ((rc = ensure_counts(ctx, 2 * nch + 2))) return rc;
+  CK(ctx->d_counters.ensure((3 * nch + 4) * sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(ctx->d_counters.p, 0, (3 * nch + 4) * sizeof(unsigned long long), ctx->stream));
+  unsigned* d_cnt = ctx->d_counters.as<unsigned>();  // [2*c] = ntasks, [2*c+1] = fetch counter
+  CK(ctx->d_tasks.ensure(ctx->task_cap * sizeof(int2)));
+  CK(ctx->d_stats.ensure((2 * nch + 2) * sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(ctx->d_stats.p, 0, (2 * nch + 2) * sizeof(unsigned long long), ctx->stream));
+  std::vector<unsigned long long> h_stats(2 * nch + 2, 0);
+  const ClassEntry* tab = class_table();
+  ctx->rec.clear();
+  ctx->st_launches = 0;
+  std::vector<int2> rec_tmp;
+  const size_t smem_rows = (size_t)2 * ns * sizeof(double);
+  const int use_smem = smem_rows <= 96 * 1024;
+  static bool enum_attr = false;
+  if (use_smem && smem_rows > 48 * 1024 && !enum_attr) {
+    CK(cudaFuncSetAttribute(k_enum, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    enum_attr = true;
+  }
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (size_t c = 0; c < nch; ++c) {
+    const Chunk& ch = chunks[c];
+    size_t ci = cp_index(ch.pca, ch.pcb);
+    int offa = T.cls_off[ch.pca], offb = T.cls_off[ch.pcb];
+    int nbra = (ch.p1 - ch.p0 + nr - 1) / nr + 1;
+    // first bra of this rank at or after p0
+    int pstart = ch.p0 + ((rk - ch.p0 % nr) % nr + nr) % nr;
+    k_enum<<<nbra, 256, use_smem ? smem_rows : 0, ctx->stream>>>(
+        T.d_ent.as<PairEntry>() + offa, T.d_ent.as<PairEntry>() + offb, T.d_Q.as<double>() + offa,
+        T.d_Q.as<double>() + offb, ctx->d_d4.as<double>() + offa, ctx->d_d4.as<double>() + offb,
+        ctx->d_ok.as<int>() + offa, ctx->d_ok.as<int>() + offb, T.d_canon.as<int>() + offa,
+        T.d_canon.as<int>() + offb, d_km.as<int>() + km_off[ci], pstart, ch.p1, nr, ch.pca == ch.pcb,
+        ctx->d_dsh.as<double>(), ns, cutoff, ctx->d_tasks.as<int2>(), d_cnt + 2 * c, (unsigned)ctx->task_cap, use_smem);
+    CK(cudaGetLastError());
+    EriArgs A;
+    fill_common_args(ctx, T, ch.pca, ch.pcb, A);
+    A.tasks = ctx->d_tasks.as<int2>();
+    A.ntasks = d_cnt + 2 * c;
+    A.counter = d_cnt + 2 * c + 1;
+    A.prim_cutoff = ctx->cut.pair * ctx->cut.pair;
+    A.cutoff = cutoff;
+    A.proj = proj_for(ctx, ch.pca, ch.pcb);
+    A.stat = ctx->d_stats.as<unsigned long long>() + 2 * c;
+    A.mode = S.mode;
+    A.nmat = S.nmat;
+    for (int m = 0; m < S.nmat; ++m) { A.DJ[m] = S.DJ[m]; A.DK[m] = S.DK[m]; A.F[m] = S.F[m]; }
+    A.cj = S.cj; A.ck = S.ck;
+    A.Pgen = S.Pgen; A.Fgen = S.Fgen; A.gen_nmat_total = S.gen_nm; A.gen_ncoul = S.gen_ncoul; A.gen_nvec = S.gen_nvec;
+    const ClassEntry& ce = tab[quartet_class(ch.pca, ch.pcb)];
+    size_t nb = std::min<size_t>((ch.cand + ce.qpb - 1) / ce.qpb, (size_t)148 * 8);
+    CK(ce.launch(A, (int)std::max<size_t>(nb, 1), ctx->stream));
+    ctx->st_launches += 2;
+    if (ctx->record) {
+      unsigned n = 0;
+      CK(cudaMemcpyAsync(&n, d_cnt + 2 * c, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      rec_tmp.resize(n);
+      CK(cudaMemcpy(rec_tmp.data(), ctx->d_tasks.p, n * sizeof(int2), cudaMemcpyDeviceToHost));
+      for (unsigned k = 0; k < n; ++k) {
+        const PairEntry& eb = T.ent[offa + rec_tmp[k].x];
+        const PairEntry& ek = T.ent[offb + rec_tmp[k].y];
+        int i = std::max(eb.sa, eb.sb), j = std::min(eb.sa, eb.sb), kk = std::max(ek.sa, ek.sb), l = std::min(ek.sa, ek.sb);
+        if ((long)i * (i + 1) / 2 + j < (long)kk * (kk + 1) / 2 + l) { std::swap(i, kk); std::swap(j, l); }
+        ctx->rec.push_back(i); ctx->rec.push_back(j); ctx->rec.push_back(kk); ctx->rec.push_back(l);
+      }
+    }
+  }
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (nch) CK(cudaMemcpyAsync(ctx->h_counts, d_cnt, 2 * nch * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  if (nch) CK(cudaMemcpyAsync(h_stats.data(), ctx->d_stats.p, 2 * nch * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->st_kernel_ms = ms;
+  long long surv = 0;
+  double flops = 0;
+  for (size_t c = 0; c < nch; ++c) {
+    unsigned n = ctx->h_counts[2 * c];
+    if (n > ctx->task_cap) { ctx->err = "task buffer overflow"; return OQPB_ERR_STATE; }
+    surv += n;
+    // algorithmic FLOPs: primitive quartets past the int_rys.F90:232 test x F_prim(class)
+    // + surviving (de-duplicated) AO integrals x digestion cost per integral
+    const Chunk& ch = chunks[c];
+    flops += (double)h_stats[2 * c] * fprim_model(PC_LA[ch.pca], PC_LB[ch.pca], PC_LA[ch.pcb], PC_LB[ch.pcb]);
+    flops += (double)h_stats[2 * c + 1] / 8.0 * S.digest_flops_per_int;
+  }
+  ctx->st_flops = flops;
+  ctx->st_survivors = surv;
+  ctx->st_skipped = total_local - surv;
+  return OQPB_OK;
+}
+
+int check_ready(oqpb_ctx* ctx) {
+  if (!ctx) return OQPB_ERR_BAD_ARG;
+  if (!ctx->have_basis || !ctx->have_cutoff || !ctx->have_screen) {
+    ctx->err = "call order: set_basis, set_cutoff, set_screening";
+    return OQPB_ERR_STATE;
+  }
+  return OQPB_OK;
+}
+
+oqpb_ctx* g_default_ctx = nullptr;
+int g_default_urohf = -1;
+
+}  // namespace
+
+// ===================================================================================== C ABI
+extern "C" {
+
+int oqpb_ctx_create(oqpb_ctx** out, int device) {
+  if (!out) return OQPB_ERR_BAD_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return OQPB_ERR_NO_DEVICE;
+  if (device < 0 || device >= ndev) return OQPB_ERR_BAD_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return OQPB_ERR_NO_DEVICE;
+  oqpb_ctx* ctx = new oqpb_ctx;
+  ctx->device = device;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return OQPB_ERR_CUDA; }
+  cudaEventCreate(&ctx->ev0);
+  cudaEventCreate(&ctx->ev1);
+  // Rys tables
+  if (ctx->d_rys.ensure(sizeof(RYS_TAB_H)) != cudaSuccess) { delete ctx; return OQPB_ERR_CUDA; }
+  cudaMemcpy(ctx->d_rys.p, RYS_TAB_H, sizeof(RYS_TAB_H), cudaMemcpyHostToDevice);
+  ctx->d_maxden.ensure(16);
+  *out = ctx;
+  return OQPB_OK;
+}
+
+void oqpb_ctx_destroy(oqpb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (g_default_ctx == ctx) g_default_ctx = nullptr;
+  free_pairtable(ctx->run);
+  for (DevBuf* b : {&ctx->d_am, &ctx->d_ncontr, &ctx->d_goff, &ctx->d_aooff, &ctx->d_naos, &ctx->d_ex, &ctx->d_cc,
+                    &ctx->d_xyz, &ctx->d_rys, &ctx->d_proj, &ctx->d_Qmat, &ctx->d_dsh, &ctx->d_maxden, &ctx->d_ok,
+                    &ctx->d_d4, &ctx->d_rowsbuf, &ctx->d_tasks, &ctx->d_counters, &ctx->d_Dsq, &ctx->d_F, &ctx->d_Din,
+                    &ctx->d_stats, &ctx->d_gen_in, &ctx->d_gen_out})
+    b->release();
+  if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* oqpb_last_error(const oqpb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int oqpb_set_basis(oqpb_ctx* ctx, int nshell, int nprim, const int* am, const int* harmonic, const int* ncontr,
+                   const int* g_offset, const int* ao_offset, const int* naos, const double* ex, const double* cc,
+                   const double* centers, int harmonic_active) {
+  if (!ctx || nshell <= 0 || nprim <= 0) return OQPB_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  ctx->nshell = nshell; ctx->nprim = nprim; ctx->harmonic_active = harmonic_active;
+  ctx->am.assign(am, am + nshell); ctx->harm.assign(harmonic, harmonic + nshell);
+  ctx->ncontr.assign(ncontr, ncontr + nshell); ctx->goff.assign(g_offset, g_offset + nshell);
+  ctx->aooff.assign(ao_offset, ao_offset + nshell); ctx->naos.assign(naos, naos + nshell);
+  ctx->ex.assign(ex, ex + nprim); ctx->cc.assign(cc, cc + nprim); ctx->cen.assign(centers, centers + 3 * nshell);
+  ctx->nbf = ao_offset[nshell - 1] + naos[nshell - 1];
+  ctx->lmax = 0;
+  int flag[4] = {-1, -1, -1, -1};
+  for (int s = 0; s < nshell; ++s) {
+    int l = am[s];
+    if (l < 0 || l > 3) { ctx->err = "angular momentum > f not supported"; return OQPB_ERR_UNSUPPORTED; }
+    ctx->lmax = std::max(ctx->lmax, l);
+    int pure = (harmonic_active && harmonic[s] == 1 && l >= 2) ? 1 : 0;
+    if (flag[l] >= 0 && flag[l] != pure) { ctx->err = "mixed harmonic flags within one angular momentum"; return OQPB_ERR_UNSUPPORTED; }
+    flag[l] = pure;
+    int expect = pure ? 2 * l + 1 : ncart(l);
+    if (naos[s] != expect) { ctx->err = "naos inconsistent with am/harmonic"; return OQPB_ERR_BAD_ARG; }
+  }
+  for (int l = 0; l < 4; ++l) ctx->pure_l[l] = flag[l] > 0;
+  if (ctx->nbf > 46000) { ctx->err = "nbf too large"; return OQPB_ERR_UNSUPPORTED; }
+  int rc;
+  if ((rc = upload(ctx, ctx->d_am, ctx->am))) return rc;
+  if ((rc = upload(ctx, ctx->d_ncontr, ctx->ncontr))) return rc;
+  if ((rc = upload(ctx, ctx->d_goff, ctx->goff))) return rc;
+  if ((rc = upload(ctx, ctx->d_aooff, ctx->aooff))) return rc;
+  if ((rc = upload(ctx, ctx->d_naos, ctx->naos))) return rc;
+  if ((rc = upload(ctx, ctx->d_ex, ctx->ex))) return rc;
+  if ((rc = upload(ctx, ctx->d_cc, ctx->cc))) return rc;
+  if ((rc = upload(ctx, ctx->d_xyz, ctx->cen))) return rc;
+  // projection tables per quartet class
+  std::vector<ProjTable> pt(55 * 4);
+  ProjTable per_l[4];
+  for (int l = 0; l < 4; ++l) build_proj(l, ctx->pure_l[l], per_l[l]);
+  for (int pa = 0; pa < NPC; ++pa)
+    for (int pb = 0; pb <= pa; ++pb) {
+      ProjTable* q = &pt[(size_t)quartet_class(pa, pb) * 4];
+      q[0] = per_l[PC_LA[pa]]; q[1] = per_l[PC_LB[pa]]; q[2] = per_l[PC_LA[pb]]; q[3] = per_l[PC_LB[pb]];
+    }
+  if ((rc = upload(ctx, ctx->d_proj, pt))) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->have_basis = true;
+  ctx->have_cutoff = ctx->have_screen = false;
+  return OQPB_OK;
+}
+
+int oqpb_set_cutoff(oqpb_ctx* ctx, double cutoff) {
+  if (!ctx || !ctx->have_basis) return OQPB_ERR_STATE;
+  cudaSetDevice(ctx->device);
+  ctx->cutoff = cutoff;
+  ctx->cut = Cutoffs{cutoff, 1.0e-2 * cutoff, 1.0e-4 * cutoff, 25.0 * std::log(10.0)};  // int2.F90:260-272
+  ctx->have_cutoff = true;
+  if (ctx->have_screen) {  // re-sort not needed, but the primitive table depends on the cutoffs
+    int rc = build_pairtable(ctx, ctx->cut, ctx->run, &ctx->Qmat);
+    if (rc) return rc;
+  }
+  return OQPB_OK;
+}
+
+int oqpb_set_screening(oqpb_ctx* ctx, const double* schwarz_in) {
+  if (!ctx || !ctx->have_basis || !ctx->have_cutoff) return OQPB_ERR_STATE;
+  cudaSetDevice(ctx->device);
+  const int ns = ctx->nshell;
+  if (schwarz_in) {
+    ctx->Qmat.assign(schwarz_in, schwarz_in + (size_t)ns * ns);
+  } else {
+    int rc = schwarz(ctx);
+    if (rc) return rc;
+  }
+  int rc = build_pairtable(ctx, ctx->cut, ctx->run, &ctx->Qmat);
+  if (rc) return rc;
+  CK(ctx->d_dsh.ensure((size_t)ns * ns * sizeof(double)));
+  ctx->have_screen = true;
+  return OQPB_OK;
+}
+
+int oqpb_get_schwarz(oqpb_ctx* ctx, double* out) {
+  if (!ctx || !ctx->have_screen) return OQPB_ERR_STATE;
+  memcpy(out, ctx->Qmat.data(), ctx->Qmat.size() * sizeof(double));
+  return OQPB_OK;
+}
+
+int oqpb_set_partition(oqpb_ctx* ctx, int rank, int nranks) {
+  if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return OQPB_ERR_BAD_ARG;
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  return OQPB_OK;
+}
+
+int oqpb_fock_dev(oqpb_ctx* ctx, int urohf, const double* d_dev, double* f_dev, int nfocks, double se, double sc) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  cudaSetDevice(ctx->device);
+  if (nfocks < 1 || nfocks > MAX_MATS - 1 || (urohf && nfocks != 2)) { ctx->err = "bad nfocks"; return OQPB_ERR_BAD_ARG; }
+  const int nbf = ctx->nbf, ns = ctx->nshell;
+  const long ntri = (long)nbf * (nbf + 1) / 2, n2 = (long)nbf * nbf;
+  const long npairs = (long)ns * (ns + 1) / 2;
+  // screening density: shlden (int2.F90:999-1047)
+  CK(cudaMemsetAsync(ctx->d_maxden.p, 0, 8, ctx->stream));
+  k_shlden_packed<<<(unsigned)((npairs + 127) / 128), 128, 0, ctx->stream>>>(
+      ns, npairs, ctx->d_aooff.as<int>(), ctx->d_naos.as<int>(), d_dev, nfocks, ntri, ctx->d_dsh.as<double>(),
+      ctx->d_maxden.as<unsigned long long>());
+  CK(cudaGetLastError());
+  // square densities
+  int nsq = nfocks + (urohf ? 1 : 0);
+  CK(ctx->d_Dsq.ensure((size_t)nsq * n2 * sizeof(double)));
+  double* Dsq = ctx->d_Dsq.as<double>();
+  for (int m = 0; m < nfocks; ++m)
+    k_expand_packed<<<(unsigned)((n2 + 255) / 256), 256, 0, ctx->stream>>>(d_dev + (size_t)m * ntri, Dsq + (size_t)m * n2, nbf);
+  if (urohf) k_add<<<(unsigned)((n2 + 255) / 256), 256, 0, ctx->stream>>>(Dsq, Dsq + n2, Dsq + 2 * n2, n2);
+  CK(cudaGetLastError());
+  CK(cudaMemsetAsync(f_dev, 0, (size_t)nfocks * ntri * sizeof(double), ctx->stream));
+  BuildSpec S;
+  S.mode = MODE_SYM;
+  S.nmat = nfocks;
+  for (int m = 0; m < nfocks; ++m) {
+    S.DJ[m] = urohf ? Dsq + 2 * n2 : Dsq + (size_t)m * n2;
+    S.DK[m] = Dsq + (size_t)m * n2;
+    S.F[m] = f_dev + (size_t)m * ntri;
+  }
+  S.cj = sc;                    // 4*sc applied in the kernel (xval4, int2.F90:1423 / 1499)
+  S.ck = urohf ? 2.0 * se : se;  // xval1 (int2.F90:1422) / xval2 (int2.F90:1498)
+  S.digest_flops_per_int = urohf ? 26.0 : 14.0 * nfocks;
+  return run_build(ctx, S);
+}
+
+int oqpb_fock_post_dev(oqpb_ctx* ctx, double* f_dev, int nfocks) {
+  if (!ctx) return OQPB_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  const long ntri = (long)ctx->nbf * (ctx->nbf + 1) / 2;
+  k_fock_post<<<(unsigned)((ntri * nfocks + 255) / 256), 256, 0, ctx->stream>>>(f_dev, ctx->nbf, ntri, nfocks);
+  CK(cudaGetLastError());
+  return OQPB_OK;
+}
+
+int oqpb_synchronize(oqpb_ctx* ctx) {
+  if (!ctx) return OQPB_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return OQPB_OK;
+}
+void* oqpb_stream(oqpb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int oqpb_fock(oqpb_ctx* ctx, int urohf, const double* d, double* f, int nfocks, double se, double sc, int post,
+              long long* nskipped) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  cudaSetDevice(ctx->device);
+  const long ntri = (long)ctx->nbf * (ctx->nbf + 1) / 2;
+  size_t bytes = (size_t)nfocks * ntri * sizeof(double);
+  CK(ctx->d_Din.ensure(bytes));
+  CK(ctx->d_F.ensure(bytes));
+  CK(cudaMemcpyAsync(ctx->d_Din.p, d, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  rc = oqpb_fock_dev(ctx, urohf, ctx->d_Din.as<double>(), ctx->d_F.as<double>(), nfocks, se, sc);
+  if (rc) return rc;
+  if (post) { rc = oqpb_fock_post_dev(ctx, ctx->d_F.as<double>(), nfocks); if (rc) return rc; }
+  CK(cudaMemcpyAsync(f, ctx->d_F.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (nskipped) *nskipped = ctx->st_skipped;
+  return OQPB_OK;
+}
+
+// shared driver for the general-density consumers: X interleaved [(nu*nbf+mu)*NM + m]
+static int gen_build(oqpb_ctx* ctx, int NM, int ncoul, int nvec, double cj, double ck) {
+  const int ns = ctx->nshell, nbf = ctx->nbf;
+  const long npairs = (long)ns * (ns + 1) / 2;
+  (void)npairs;
+  CK(cudaMemsetAsync(ctx->d_gen_out.p, 0, (size_t)nbf * nbf * NM * sizeof(double), ctx->stream));
+  BuildSpec S;
+  S.mode = MODE_GEN;
+  S.Pgen = ctx->d_gen_in.as<double>();
+  S.Fgen = ctx->d_gen_out.as<double>();
+  S.gen_nm = NM; S.gen_ncoul = ncoul; S.gen_nvec = nvec;
+  S.cj = cj; S.ck = ck;
+  S.digest_flops_per_int = (ncoul > 0 ? 144.0 / 7.0 : 16.0) * NM;  // MRSF: (4*4+8*7)*2 per vector; TD: 24 per vector
+  return run_build(ctx, S);
+}
+
+int oqpb_jk_td(oqpb_ctx* ctx, const double* d2, int nvec, int flags, double se, double sc, double* apb, double* amb,
+               long long* nskipped) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  cudaSetDevice(ctx->device);
+  if (nvec < 1) return OQPB_ERR_BAD_ARG;
+  const int ns = ctx->nshell, nbf = ctx->nbf;
+  const long n2 = (long)nbf * nbf, npairs = (long)ns * (ns + 1) / 2;
+  const bool tda = flags & OQPB_TD_TDA;
+  const bool want_apb = !tda && (flags & OQPB_TD_APB), want_amb = tda || (flags & OQPB_TD_AMB);
+  size_t bytes = (size_t)n2 * nvec * sizeof(double);
+  CK(ctx->d_Din.ensure(bytes));
+  CK(cudaMemcpyAsync(ctx->d_Din.p, d2, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  // screening density from the caller's d2 itself: shltd (tdhf_lib.F90:300-325); d2 (mu,nu,v) has v slowest,
+  // so screen on a plain interleaved copy first
+  int ncomp = tda ? 1 : ((want_apb ? 1 : 0) + (want_amb ? 1 : 0));
+  if (ncomp == 0) return OQPB_ERR_BAD_ARG;
+  int NM = nvec * (tda ? 1 : 2);
+  CK(ctx->d_gen_in.ensure((size_t)n2 * NM * sizeof(double)));
+  CK(ctx->d_gen_out.ensure((size_t)n2 * NM * sizeof(double)));
+  unsigned gb = (unsigned)((n2 * nvec + 255) / 256);
+  // plain copy for screening (stored in d_gen_out temporarily)
+  k_td_pack<<<gb, 256, 0, ctx->stream>>>(ctx->d_Din.as<double>(), ctx->d_gen_out.as<double>(), nbf, nvec, 1, 0);
+  CK(cudaMemsetAsync(ctx->d_maxden.p, 0, 8, ctx->stream));
+  k_shlden_gen<<<(unsigned)((npairs + 127) / 128), 128, 0, ctx->stream>>>(
+      ns, npairs, ctx->d_aooff.as<int>(), ctx->d_naos.as<int>(), ctx->d_gen_out.as<double>(), nvec, nbf,
+      ctx->d_dsh.as<double>(), ctx->d_maxden.as<unsigned long long>());
+  CK(cudaGetLastError());
+  if (tda) {
+    // amb = -se K[P] (+ 2 sc J[P+P^T] on 4 targets): tdhf_lib.F90:169-186
+    k_td_pack<<<gb, 256, 0, ctx->stream>>>(ctx->d_Din.as<double>(), ctx->d_gen_in.as<double>(), nbf, nvec, 1, 0);
+    rc = gen_build(ctx, NM, (flags & OQPB_TD_TDA_COULOMB) ? 1 : 0, nvec, 2.0 * sc, se);
+    if (rc) return rc;
+    k_td_unpack<<<gb, 256, 0, ctx->stream>>>(ctx->d_gen_out.as<double>(), ctx->d_Din.as<double>(), nbf, nvec, NM, 0);
+    CK(cudaMemcpyAsync(amb, ctx->d_Din.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    // comp 0: Ps = P+P^T -> apb (Coulomb 4 sc, exchange se, symmetrised); comp 1: Pa = P-P^T -> amb (exchange only)
+    k_td_pack<<<gb, 256, 0, ctx->stream>>>(ctx->d_Din.as<double>(), ctx->d_gen_in.as<double>(), nbf, nvec, 2, 1);
+    rc = gen_build(ctx, NM, want_apb ? 1 : 0, nvec, 2.0 * sc, se);
+    if (rc) return rc;
+    if (want_apb) {
+      k_td_unpack<<<gb, 256, 0, ctx->stream>>>(ctx->d_gen_out.as<double>(), ctx->d_Din.as<double>(), nbf, nvec, NM, 0);
+      CK(cudaMemcpyAsync(apb, ctx->d_Din.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (want_amb) {
+      k_td_unpack<<<gb, 256, 0, ctx->stream>>>(ctx->d_gen_out.as<double>(), ctx->d_Din.as<double>(), nbf, nvec, NM, 1);
+      CK(cudaMemcpyAsync(amb, ctx->d_Din.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (nskipped) *nskipped = ctx->st_skipped;
+  return OQPB_OK;
+}
+
+int oqpb_jk_mrsf(oqpb_ctx* ctx, const double* d3, int nvec, int ncomp, double se, double sc, double* f3,
+                 long long* nskipped) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  cudaSetDevice(ctx->device);
+  if (nvec < 1 || ncomp < 4) return OQPB_ERR_BAD_ARG;
+  const int ns = ctx->nshell, nbf = ctx->nbf;
+  const long n2 = (long)nbf * nbf, npairs = (long)ns * (ns + 1) / 2;
+  const int NM = nvec * ncomp;
+  size_t bytes = (size_t)n2 * NM * sizeof(double);
+  CK(ctx->d_gen_in.ensure(bytes));
+  CK(ctx->d_gen_out.ensure(bytes));
+  CK(cudaMemcpyAsync(ctx->d_gen_in.p, d3, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_maxden.p, 0, 8, ctx->stream));
+  k_shlden_gen<<<(unsigned)((npairs + 127) / 128), 128, 0, ctx->stream>>>(
+      ns, npairs, ctx->d_aooff.as<int>(), ctx->d_naos.as<int>(), ctx->d_gen_in.as<double>(), NM, nbf,
+      ctx->d_dsh.as<double>(), ctx->d_maxden.as<unsigned long long>());
+  CK(cudaGetLastError());
+  // Coulomb: cval * ds with ds = d3 + d3^T on (i,j),(j,i),(k,l),(l,k)  -> cj = sc; exchange xval -> ck = se
+  rc = gen_build(ctx, NM, 4, nvec, sc, se);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(f3, ctx->d_gen_out.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (nskipped) *nskipped = ctx->st_skipped;
+  return OQPB_OK;
+}
+
+int oqpb_last_stats(oqpb_ctx* ctx, long long* s) {
+  if (!ctx) return OQPB_ERR_BAD_ARG;
+  s[0] = ctx->st_survivors; s[1] = ctx->st_skipped; s[2] = 0; s[3] = ctx->st_launches;
+  return OQPB_OK;
+}
+double oqpb_last_flops(oqpb_ctx* ctx) { return ctx ? ctx->st_flops : 0.0; }
+double oqpb_last_kernel_ms(oqpb_ctx* ctx) { return ctx ? ctx->st_kernel_ms : 0.0; }
+
+int oqpb_record_quartets(oqpb_ctx* ctx, int enable) {
+  if (!ctx) return OQPB_ERR_BAD_ARG;
+  ctx->record = enable != 0;
+  return OQPB_OK;
+}
+long long oqpb_get_quartets(oqpb_ctx* ctx, int* ijkl, long long maxq) {
+  if (!ctx) return -1;
+  long long n = (long long)ctx->rec.size() / 4;
+  if (ijkl) memcpy(ijkl, ctx->rec.data(), (size_t)std::min(n, maxq) * 4 * sizeof(int));
+  return n;
+}
+
+int oqpb_get_shell_density(oqpb_ctx* ctx, double* dsh, double* max_den) {
+  if (!ctx || !ctx->have_screen) return OQPB_ERR_STATE;
+  cudaSetDevice(ctx->device);
+  CK(cudaMemcpy(dsh, ctx->d_dsh.p, (size_t)ctx->nshell * ctx->nshell * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(max_den, ctx->d_maxden.p, sizeof(double), cudaMemcpyDeviceToHost));
+  return OQPB_OK;
+}
+
+int oqpb_eri_block(oqpb_ctx* ctx, int i, int j, int k, int l, double* out, int* nout) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  cudaSetDevice(ctx->device);
+  const PairTable& T = ctx->run;
+  auto find = [&](int a, int b, int& pc, int& idx) {
+    int la = ctx->am[a], lb = ctx->am[b];
+    pc = la >= lb ? pair_class(la, lb) : pair_class(lb, la);
+    int hi = std::max(a, b), lo = std::min(a, b);
+    int canon = hi * (hi + 1) / 2 + lo;
+    for (int e = T.cls_off[pc]; e < T.cls_off[pc + 1]; ++e)
+      if (T.canon[e] == canon) { idx = e - T.cls_off[pc]; return; }
+    idx = -1;
+  };
+  int pca, pcb, ea, eb;
+  find(i, j, pca, ea);
+  find(k, l, pcb, eb);
+  bool swapped = pca < pcb;
+  if (swapped) { std::swap(pca, pcb); std::swap(ea, eb); }
+  DevBuf d_task, d_cnt, d_out;
+  int2 task = make_int2(ea, eb);
+  unsigned cnt[2] = {1, 0};
+  CK(d_task.ensure(sizeof(int2)));
+  CK(d_cnt.ensure(sizeof cnt));
+  CK(d_out.ensure(10000 * sizeof(double)));
+  CK(cudaMemcpy(d_task.p, &task, sizeof task, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_cnt.p, cnt, sizeof cnt, cudaMemcpyHostToDevice));
+  EriArgs A;
+  fill_common_args(ctx, T, pca, pcb, A);
+  A.tasks = d_task.as<int2>();
+  A.ntasks = d_cnt.as<unsigned>();
+  A.counter = d_cnt.as<unsigned>() + 1;
+  A.prim_cutoff = ctx->cut.pair * ctx->cut.pair;
+  A.proj = proj_for(ctx, pca, pcb);
+  A.mode = MODE_BLOCK;
+  A.blockout = d_out.as<double>();
+  const ClassEntry& ce = class_table()[quartet_class(pca, pcb)];
+  CK(ce.launch(A, 1, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  // kernel block order: (A,B,C,D) = (bra.sa, bra.sb, ket.sa, ket.sb); map back to the caller's (i,j,k,l)
+  const PairEntry& pb = T.ent[T.cls_off[pca] + ea];
+  const PairEntry& pk = T.ent[T.cls_off[pcb] + eb];
+  int sh[4] = {pb.sa, pb.sb, pk.sa, pk.sb};
+  int dims[4];
+  for (int s = 0; s < 4; ++s) dims[s] = ctx->naos[sh[s]];
+  std::vector<double> blk((size_t)dims[0] * dims[1] * dims[2] * dims[3]);
+  CK(cudaMemcpy(blk.data(), d_out.p, blk.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  int want[4] = {i, j, k, l};
+  // position of each caller index in kernel order
+  int pos[4];
+  bool used[4] = {false, false, false, false};
+  int braw[2] = {swapped ? 2 : 0, swapped ? 3 : 1};  // caller positions forming the kernel's bra
+  int ketw[2] = {swapped ? 0 : 2, swapped ? 1 : 3};
+  // bra: kernel slots 0,1 ; ket: slots 2,3
+  auto assign = [&](int w0, int w1, int s0, int s1) {
+    if (want[w0] == sh[s0] && want[w1] == sh[s1] && !(want[w0] == want[w1] && false)) { pos[w0] = s0; pos[w1] = s1; }
+    else { pos[w0] = s1; pos[w1] = s0; }
+  };
+  assign(braw[0], braw[1], 0, 1);
+  assign(ketw[0], ketw[1], 2, 3);
+  (void)used;
+  int nd[4];
+  for (int w = 0; w < 4; ++w) nd[w] = dims[pos[w]];
+  for (int w = 0; w < 4; ++w) nout[w] = nd[w];
+  int c[4];
+  for (c[0] = 0; c[0] < nd[0]; ++c[0])
+    for (c[1] = 0; c[1] < nd[1]; ++c[1])
+      for (c[2] = 0; c[2] < nd[2]; ++c[2])
+        for (c[3] = 0; c[3] < nd[3]; ++c[3]) {
+          int kidx[4];
+          for (int w = 0; w < 4; ++w) kidx[pos[w]] = c[w];
+          out[((c[0] * nd[1] + c[1]) * nd[2] + c[2]) * nd[3] + c[3]] =
+              blk[(((size_t)kidx[0] * dims[1] + kidx[1]) * dims[2] + kidx[2]) * dims[3] + kidx[3]];
+        }
+  d_task.release(); d_cnt.release(); d_out.release();
+  return OQPB_OK;
+}
+
+int oqpb_rys(oqpb_ctx* ctx, int nroots, int npts, const double* x, double* t2, double* w) {
+  if (!ctx || nroots < 1 || nroots > RYS_MAXR) return OQPB_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  DevBuf dx, dt, dw;
+  CK(dx.ensure(npts * sizeof(double)));
+  CK(dt.ensure((size_t)npts * nroots * sizeof(double)));
+  CK(dw.ensure((size_t)npts * nroots * sizeof(double)));
+  CK(cudaMemcpy(dx.p, x, npts * sizeof(double), cudaMemcpyHostToDevice));
+  EriArgs A;
+  memset(&A, 0, sizeof A);
+  A.rys_tab = ctx->d_rys.as<double>() + RYS_OFF_H[nroots - 1];
+  A.rys_xmax = RYS_XMAX_H[nroots - 1];
+  for (int k = 0; k < 7; ++k) { A.herm_r[k] = RYS_HERM_R_H[nroots - 1][k]; A.herm_w[k] = RYS_HERM_W_H[nroots - 1][k]; }
+  k_rys_test<<<(npts + 127) / 128, 128, 0, ctx->stream>>>(A, nroots, npts, dx.as<double>(), dt.as<double>(), dw.as<double>());
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(t2, dt.p, (size_t)npts * nroots * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(w, dw.p, (size_t)npts * nroots * sizeof(double), cudaMemcpyDeviceToHost));
+  dx.release(); dt.release(); dw.release();
+  return OQPB_OK;
+}
+
+double oqpb_fp64_peak_tflops(oqpb_ctx* ctx) {
+  if (!ctx) return 0.0;
+  if (ctx->fp64_peak > 0) return ctx->fp64_peak;
+  cudaSetDevice(ctx->device);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, ctx->device);
+  int nb = prop.multiProcessorCount * 8, nt = 256, iters = 1 << 16;
+  double* d = nullptr;
+  if (cudaMalloc(&d, (size_t)nb * nt * sizeof(double)) != cudaSuccess) return 0.0;
+  k_fp64_peak<<<nb, nt, 0, ctx->stream>>>(d, 1024);
+  cudaStreamSynchronize(ctx->stream);
+  double best = 0;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    k_fp64_peak<<<nb, nt, 0, ctx->stream>>>(d, iters);
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    double tf = 2.0 * 8.0 * (double)iters * nb * nt / (ms * 1e-3) / 1e12;
+    best = std::max(best, tf);
+  }
+  cudaFree(d);
+  ctx->fp64_peak = best;
+  return best;
+}
+
+int oqpb_set_default_ctx(oqpb_ctx* ctx) { g_default_ctx = ctx; return OQPB_OK; }
+int oqpb_set_default_scftype(int urohf) { g_default_urohf = urohf; return OQPB_OK; }
+
+// routec_fock_jk: signature and semantics of routec_bridge.F90:33-40 (f returned ready to use, info != 0 -> native)
+void routec_fock_jk(const double* d, double* f, const int* nbf, const int* nfocks, const double* se, const double* sc,
+                    int* info) {
+  if (info) *info = 1;
+  oqpb_ctx* ctx = g_default_ctx;
+  if (!ctx || !d || !f || !nbf || !nfocks || !se || !sc) return;
+  if (*nbf != ctx->nbf) return;
+  int urohf = g_default_urohf >= 0 ? g_default_urohf : (*nfocks == 2 ? 1 : 0);
+  int rc = oqpb_fock(ctx, urohf, d, f, *nfocks, *se, *sc, 1, nullptr);
+  if (info) *info = rc;
+}
+
+}  // extern "C"

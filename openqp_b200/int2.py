@@ -1,0 +1,271 @@
+"""Host-side mirror of the reference's two-electron driver interface, on top of the C ABI
+(include/oqp_b200.h, libopenqp_b200.so).  The reference host is Fortran (no Fortran compiler in this image),
+so this mirror is Python over ctypes; `fortran/oqp_b200_shim.F90` is the ISO_C_BINDING shim a maintainer
+would compile into OpenQP.
+
+Names follow /root/reference/source/integrals/int2.F90:137-185:
+    Int2Compute.init / set_screening / set_cutoff / run(consumer) / clean, field `skipped`
+    consumers Int2RhfData, Int2UrohfData (int2.F90:83-135), Int2TdData (tdhf_lib.F90:11-31),
+    Int2MrsfData (tdhf_mrsf_lib.F90:8-26); `fock_jk` (scf_addons.F90:1063-1214).
+
+There is NO CPU fallback: a missing library or a missing CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "libopenqp_b200.so")
+_LIB = None
+
+OQPB_TD_APB, OQPB_TD_AMB, OQPB_TD_TDA, OQPB_TD_TDA_COULOMB = 1, 2, 4, 8
+
+_ERRORS = {1: "no CUDA device", 2: "bad argument", 3: "unsupported", 4: "call order", 5: "CUDA error"}
+
+
+class Int2Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libopenqp_b200.so (built in-tree by openqp_b200.build); raises if it is missing."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_LIBPATH):
+            raise Int2Error(f"{_LIBPATH} not built: run `python -m openqp_b200.build` (no CPU fallback exists)")
+        L = C.CDLL(_LIBPATH)
+        L.oqpb_last_error.restype = C.c_char_p
+        L.oqpb_last_flops.restype = C.c_double
+        L.oqpb_last_kernel_ms.restype = C.c_double
+        L.oqpb_fp64_peak_tflops.restype = C.c_double
+        L.oqpb_get_quartets.restype = C.c_longlong
+        L.oqpb_stream.restype = C.c_void_p
+        for name in ("oqpb_last_error", "oqpb_last_flops", "oqpb_last_kernel_ms", "oqpb_fp64_peak_tflops",
+                     "oqpb_ctx_destroy", "oqpb_stream", "oqpb_synchronize"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class Int2Compute:
+    """int2_compute_t (int2.F90:137-185)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        rc = lib().oqpb_ctx_create(C.byref(self._h), C.c_int(device))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise Int2Error(f"oqpb_ctx_create failed: {_ERRORS.get(rc, rc)} (this library has no CPU fallback)")
+        self.device = device
+        self.basis = None
+        self.skipped = 0
+        self.cutoff = None
+
+    # -- error handling ---------------------------------------------------------------------------
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = lib().oqpb_last_error(self._h)
+            raise Int2Error(f"{what}: {_ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    # -- int2_compute_t%init (int2.F90:245-289) -----------------------------------------------------
+    def init(self, basis, cutoff: float = 5e-11):
+        b = basis
+        self.basis = b
+        self._check(lib().oqpb_set_basis(
+            self._h, C.c_int(b.nshell), C.c_int(b.nprim), _ip(b.am), _ip(b.harmonic), _ip(b.ncontr), _ip(b.g_offset),
+            _ip(b.ao_offset), _ip(b.naos), _dp(b.ex), _dp(b.cc), _dp(b.centers), C.c_int(1 if b.spherical else 0)),
+            "oqpb_set_basis")
+        self.set_cutoff(cutoff)
+        return self
+
+    def set_cutoff(self, cutoff: float):
+        self.cutoff = float(cutoff)
+        self._check(lib().oqpb_set_cutoff(self._h, C.c_double(cutoff)), "oqpb_set_cutoff")
+
+    # -- int2_compute_t%set_screening (int2.F90:473-477) -------------------------------------------
+    def set_screening(self, schwarz=None):
+        if schwarz is None:
+            self._check(lib().oqpb_set_screening(self._h, None), "oqpb_set_screening")
+        else:
+            q = np.ascontiguousarray(schwarz, dtype=np.float64)
+            assert q.shape == (self.basis.nshell, self.basis.nshell)
+            self._check(lib().oqpb_set_screening(self._h, _dp(q)), "oqpb_set_screening")
+        return self.schwarz()
+
+    def schwarz(self):
+        ns = self.basis.nshell
+        q = np.zeros((ns, ns))
+        self._check(lib().oqpb_get_schwarz(self._h, _dp(q)), "oqpb_get_schwarz")
+        return q
+
+    def set_partition(self, rank: int, nranks: int):
+        self._check(lib().oqpb_set_partition(self._h, C.c_int(rank), C.c_int(nranks)), "oqpb_set_partition")
+
+    # -- int2_compute_t%run (int2.F90:500, 589) ---------------------------------------------------
+    def run(self, consumer):
+        consumer._run(self)
+        self.skipped = consumer.skipped
+        return consumer
+
+    def clean(self):
+        if self._h:
+            lib().oqpb_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.clean()
+        except Exception:
+            pass
+
+    # -- device-pointer entry points (bench / NCCL) -------------------------------------------------
+    def fock_dev(self, d_ptr: int, f_ptr: int, nfocks: int, urohf=False, scale_exchange=1.0, scale_coulomb=1.0):
+        self._check(lib().oqpb_fock_dev(self._h, C.c_int(1 if urohf else 0), C.c_void_p(d_ptr), C.c_void_p(f_ptr),
+                                        C.c_int(nfocks), C.c_double(scale_exchange), C.c_double(scale_coulomb)),
+                    "oqpb_fock_dev")
+
+    def fock_post_dev(self, f_ptr: int, nfocks: int):
+        self._check(lib().oqpb_fock_post_dev(self._h, C.c_void_p(f_ptr), C.c_int(nfocks)), "oqpb_fock_post_dev")
+
+    def synchronize(self):
+        self._check(lib().oqpb_synchronize(self._h), "oqpb_synchronize")
+
+    def stream(self) -> int:
+        return lib().oqpb_stream(self._h)
+
+    # -- introspection --------------------------------------------------------------------------
+    def last_stats(self):
+        s = (C.c_longlong * 4)()
+        lib().oqpb_last_stats(self._h, s)
+        return {"nquartets": int(s[0]), "nschwz": int(s[1]), "launches": int(s[3]),
+                "flops": lib().oqpb_last_flops(self._h), "kernel_ms": lib().oqpb_last_kernel_ms(self._h)}
+
+    def record_quartets(self, enable=True):
+        lib().oqpb_record_quartets(self._h, C.c_int(1 if enable else 0))
+
+    def quartets(self):
+        n = lib().oqpb_get_quartets(self._h, None, C.c_longlong(0))
+        out = np.zeros((n, 4), dtype=np.int32)
+        if n:
+            lib().oqpb_get_quartets(self._h, _ip(out), C.c_longlong(n))
+        return out
+
+    def shell_density(self):
+        ns = self.basis.nshell
+        dsh = np.zeros((ns, ns))
+        mx = C.c_double(0)
+        self._check(lib().oqpb_get_shell_density(self._h, _dp(dsh), C.byref(mx)), "oqpb_get_shell_density")
+        return dsh, mx.value
+
+    def eri_block(self, i, j, k, l):
+        out = np.zeros(10000)
+        n = np.zeros(4, dtype=np.int32)
+        self._check(lib().oqpb_eri_block(self._h, C.c_int(i), C.c_int(j), C.c_int(k), C.c_int(l), _dp(out), _ip(n)),
+                    "oqpb_eri_block")
+        return out[: int(np.prod(n))].reshape(tuple(int(x) for x in n)).copy()
+
+    def rys(self, nroots, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        t2 = np.zeros((len(x), nroots))
+        w = np.zeros((len(x), nroots))
+        self._check(lib().oqpb_rys(self._h, C.c_int(nroots), C.c_int(len(x)), _dp(x), _dp(t2), _dp(w)), "oqpb_rys")
+        return t2, w
+
+    def fp64_peak_tflops(self) -> float:
+        return lib().oqpb_fp64_peak_tflops(self._h)
+
+
+# ------------------------------------------------------------------------------------------- consumers
+class Int2RhfData:
+    """int2_rhf_data_t (int2.F90:1414-1484): d, f packed (nfocks, ntri); f = raw accumulator unless post."""
+    urohf = False
+
+    def __init__(self, d, scale_exchange=1.0, scale_coulomb=1.0, post=False):
+        self.d = np.ascontiguousarray(np.atleast_2d(d), dtype=np.float64)
+        self.scale_exchange = scale_exchange
+        self.scale_coulomb = scale_coulomb
+        self.post = post
+        self.f = None
+        self.skipped = 0
+
+    def _run(self, drv: Int2Compute):
+        nf, ntri = self.d.shape
+        assert ntri == drv.basis.ntri
+        self.f = np.zeros_like(self.d)
+        ns = C.c_longlong(0)
+        drv._check(lib().oqpb_fock(drv._h, C.c_int(1 if self.urohf else 0), _dp(self.d), _dp(self.f), C.c_int(nf),
+                                   C.c_double(self.scale_exchange), C.c_double(self.scale_coulomb),
+                                   C.c_int(1 if self.post else 0), C.byref(ns)), "oqpb_fock")
+        self.skipped = int(ns.value)
+
+
+class Int2UrohfData(Int2RhfData):
+    """int2_urohf_data_t (int2.F90:1488-1578): d(ntri,2) = alpha, beta."""
+    urohf = True
+
+
+class Int2TdData:
+    """int2_td_data_t (tdhf_lib.F90:11-31).  d2: (nvec, nbf, nbf) with d2[v][mu, nu]; results apb, amb likewise
+    (apb symmetrised as in parallel_stop, tdhf_lib.F90:107-109)."""
+
+    def __init__(self, d2, int_apb=True, int_amb=False, tamm_dancoff=False, tamm_dancoff_coulomb=False,
+                 scale_exchange=1.0, scale_coulomb=1.0):
+        self.d2 = np.asarray(d2, dtype=np.float64)
+        self.int_apb, self.int_amb = int_apb, int_amb
+        self.tamm_dancoff, self.tamm_dancoff_coulomb = tamm_dancoff, tamm_dancoff_coulomb
+        self.scale_exchange, self.scale_coulomb = scale_exchange, scale_coulomb
+        self.apb = self.amb = None
+        self.skipped = 0
+
+    def _run(self, drv: Int2Compute):
+        nv, nbf, _ = self.d2.shape
+        dF = np.ascontiguousarray(np.transpose(self.d2, (0, 2, 1)))  # Fortran (mu, nu, v): mu fastest
+        apb = np.zeros_like(dF)
+        amb = np.zeros_like(dF)
+        flags = ((OQPB_TD_APB if self.int_apb else 0) | (OQPB_TD_AMB if self.int_amb else 0) |
+                 (OQPB_TD_TDA if self.tamm_dancoff else 0) | (OQPB_TD_TDA_COULOMB if self.tamm_dancoff_coulomb else 0))
+        ns = C.c_longlong(0)
+        drv._check(lib().oqpb_jk_td(drv._h, _dp(dF), C.c_int(nv), C.c_int(flags), C.c_double(self.scale_exchange),
+                                    C.c_double(self.scale_coulomb), _dp(apb), _dp(amb), C.byref(ns)), "oqpb_jk_td")
+        self.apb = np.transpose(apb, (0, 2, 1)).copy()
+        self.amb = np.transpose(amb, (0, 2, 1)).copy()
+        self.skipped = int(ns.value)
+
+
+class Int2MrsfData:
+    """int2_mrsf_data_t (tdhf_mrsf_lib.F90:8-26).  d3: (nvec, ncomp, nbf, nbf) [v, c, mu, nu]; f3 likewise."""
+
+    def __init__(self, d3, scale_exchange=1.0, scale_coulomb=1.0):
+        self.d3 = np.asarray(d3, dtype=np.float64)
+        self.scale_exchange, self.scale_coulomb = scale_exchange, scale_coulomb
+        self.f3 = None
+        self.skipped = 0
+
+    def _run(self, drv: Int2Compute):
+        nv, nc, nbf, _ = self.d3.shape
+        dF = np.ascontiguousarray(np.transpose(self.d3, (3, 2, 1, 0)))  # Fortran d3(v, c, mu, nu): v fastest
+        f3 = np.zeros_like(dF)
+        ns = C.c_longlong(0)
+        drv._check(lib().oqpb_jk_mrsf(drv._h, _dp(dF), C.c_int(nv), C.c_int(nc), C.c_double(self.scale_exchange),
+                                      C.c_double(self.scale_coulomb), _dp(f3), C.byref(ns)), "oqpb_jk_mrsf")
+        self.f3 = np.transpose(f3, (3, 2, 1, 0)).copy()
+        self.skipped = int(ns.value)
+
+
+def fock_jk(drv: Int2Compute, d, scale_exchange=1.0, scale_coulomb=1.0, urohf=False):
+    """fock_jk (scf_addons.F90:1063-1214): packed d (nfocks, ntri) -> packed f, ready to use
+    (0.5 scaling and diagonal doubling applied, :1177-1185); returns (f, nschwz)."""
+    cons = (Int2UrohfData if urohf else Int2RhfData)(d, scale_exchange, scale_coulomb, post=True)
+    drv.run(cons)
+    return cons.f, cons.skipped

@@ -59,7 +59,10 @@ double pnrm2(int l, int c) {
 //  nodes^2 / weights; both are recomputed here by Newton iteration instead of being copied).
 constexpr int MXRYS = 13;
 const int NAUXS[MXRYS] = {20, 25, 30, 30, 35, 40, 40, 40, 45, 50, 50, 55, 55};  // rys_lut.F90:8-9
-const double XASYMP[MXRYS] = {29, 37, 43, 49, 55, 60, 65, 71, 76, 81, 86, 91, 96};  // rys_lut.F90:12-17
+// rys_lut.F90:12-17 switch points + 10.  At the reference's own switch points the Hermite asymptote is
+// only ~1.5e-12 accurate; the reference's nroots<=5 fits (not restated) are ~1e-14 accurate there, so the
+// oracle delays the switch to stay at fit-level accuracy for every nroots.
+const double XASYMP[MXRYS] = {39, 47, 53, 59, 65, 70, 75, 81, 86, 91, 96, 101, 106};
 
 struct RysTables {
   std::vector<double> raux[MXRYS], waux[MXRYS];  // per nroots

@@ -1,0 +1,270 @@
+"""GPU: parity of the CUDA path (through the C ABI) against the oracle, the committed golden vectors and the
+reference's golden energies.  Tolerances: integer/list work bit-exact; Fock elements 1e-10 Eh absolute;
+SCF energies 1e-8 Eh (BASELINE.json north_star)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from common import decaying_density, golden, random_sym_density, rpa_energies
+from openqp_b200 import basis as B
+from openqp_b200.scf import pack, scf, unpack
+
+pytestmark = pytest.mark.gpu
+
+FOCK_TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def drv():
+    from openqp_b200.int2 import Int2Compute
+    d = Int2Compute(0)
+    yield d
+    d.clean()
+
+
+def _pair(oracle_mod, drv, mol, basis, cutoff=5e-11, upload_q=False):
+    bs = B.BasisSet(mol, basis)
+    o = oracle_mod.Oracle(bs, cutoff)
+    q = o.set_screening()
+    drv.init(bs, cutoff)
+    drv.set_screening(q if upload_q else None)
+    return bs, o
+
+
+def test_rys_tables_vs_oracle(oracle_mod, drv):
+    for R in range(1, 8):
+        x = np.concatenate([np.linspace(0, 80, 161), [1e-9, 38.999, 39.0, 74.999, 75.0, 150.0, 1e3]])
+        t2, w = drv.rys(R, x)
+        for i, xx in enumerate(x):
+            u, ww = oracle_mod.rys(R, xx)
+            o = np.argsort(u)
+            assert np.abs(t2[i] - (u / (1 + u))[o]).max() < 5e-13, (R, xx)
+            assert np.abs(w[i] / ww[o] - 1).max() < 5e-12, (R, xx)
+
+
+@pytest.mark.parametrize("basis", ["6-31g(d)", "cc-pvdz", "cc-pvtz"])
+def test_schwarz_matrix(oracle_mod, drv, basis):
+    """ints_exchange (int2.F90:1582-1737) on the device."""
+    bs, o = _pair(oracle_mod, drv, B.water_dimer(), basis)
+    qg, qo = drv.schwarz(), o.schwarz
+    assert np.abs(qg - qo).max() < 1e-12
+    assert np.abs(qg / qo - 1).max() < 1e-11
+
+
+@pytest.mark.parametrize("basis", ["6-31g(d)", "cc-pvtz"])
+def test_eri_blocks(oracle_mod, drv, basis):
+    """shellquartet (int2.F90:1051-1183): every angular-momentum class, all index orders."""
+    bs, o = _pair(oracle_mod, drv, B.water(), basis)
+    rng = np.random.default_rng(0)
+    seen = set()
+    for it in range(400):
+        i, j, k, l = (int(x) for x in rng.integers(0, bs.nshell, 4))
+        key = tuple(sorted((tuple(sorted((bs.am[i], bs.am[j]))), tuple(sorted((bs.am[k], bs.am[l]))))))
+        if key in seen and it > 150:
+            continue
+        seen.add(key)
+        ci, cj, ck, cl = max(i, j), min(i, j), max(k, l), min(k, l)
+        bo = o.eri_block(ci, cj, ck, cl)  # the reference engine is only ever called with i>=j, k>=l
+        if i < j:
+            bo = bo.transpose(1, 0, 2, 3)
+        if k < l:
+            bo = bo.transpose(0, 1, 3, 2)
+        bg = drv.eri_block(i, j, k, l)
+        assert bg.shape == bo.shape
+        assert np.abs(bg - bo).max() < 2e-12, (i, j, k, l, bs.am[[i, j, k, l]])
+    assert len(seen) >= (15 if basis == "6-31g(d)" else 40)
+
+
+@pytest.mark.parametrize("basis", ["6-31g(d)", "cc-pvtz"])
+def test_fock_vs_committed_golden(drv, basis):
+    """no live oracle: compare against tests/golden/oracle_fock_h2o.json"""
+    from openqp_b200.int2 import fock_jk
+    g = golden("oracle_fock_h2o.json")[basis]
+    bs = B.BasisSet(B.water(), basis)
+    drv.init(bs)
+    q = drv.set_screening()
+    assert abs(q.sum() - g["schwarz_sum"]) < 1e-9
+    d = random_sym_density(bs.nbf, g["seed"])
+    f, nschwz = fock_jk(drv, pack(d))
+    assert np.abs(f[0] - np.array(g["fock"])).max() < FOCK_TOL
+    assert nschwz == g["stats"]["nschwz"]
+    assert drv.last_stats()["nquartets"] == g["stats"]["nquartets"]
+
+
+@pytest.mark.parametrize("molname,basis", [("benzene", "cc-pvdz"), ("dimer", "cc-pvtz"), ("benzene", "6-31g(d)")])
+def test_fock_rhf_and_screening_bit_exact(oracle_mod, drv, molname, basis):
+    """int2_twoei + int2_rhf_data_t (int2.F90:589-923, 1414-1484) with a decaying density so that screening bites.
+    With the oracle's Schwarz matrix uploaded the surviving quartet set must be identical."""
+    from openqp_b200.int2 import Int2RhfData
+    mol = B.benzene() if molname == "benzene" else B.water_dimer()
+    bs, o = _pair(oracle_mod, drv, mol, basis, upload_q=True)
+    dm = decaying_density(bs) * (1e-4 if molname == "benzene" else 1e-2)
+    d = pack(dm)
+    lst, n, nschwz = o.quartet_list(d)
+    drv.record_quartets(True)
+    cons = drv.run(Int2RhfData(d, scale_exchange=0.2, scale_coulomb=1.0))  # B3LYP-like hybrid (config 2)
+    drv.record_quartets(False)
+    assert cons.skipped == nschwz and nschwz > 0
+    got = drv.quartets()
+    assert got.shape == lst.shape
+    key = lambda a: a[np.lexsort(a.T[::-1])]
+    assert np.array_equal(key(got), key(lst))  # bit-exact surviving quartet list
+    dsh_g, md_g = drv.shell_density()
+    dsh_o, md_o = o.shlden(0, np.atleast_2d(d), 1)
+    assert np.array_equal(dsh_g, dsh_o) and md_g == md_o  # shlden (int2.F90:999-1047) bit-exact
+    f, st = o.fock(d, scale_exchange=0.2, scale_coulomb=1.0, post=False)
+    assert np.abs(cons.f - f).max() < FOCK_TOL * max(1.0, 0.0)
+    # same build with the device-computed Schwarz matrix: counts may differ only through ulp-level Q differences
+    drv.set_screening(None)
+    cons2 = drv.run(Int2RhfData(d, scale_exchange=0.2, scale_coulomb=1.0))
+    assert abs(cons2.skipped - nschwz) <= max(2, nschwz // 100000)
+    assert np.abs(cons2.f - f).max() < FOCK_TOL
+
+
+def test_fock_urohf(oracle_mod, drv):
+    """int2_urohf_data_t (int2.F90:1488-1578)."""
+    from openqp_b200.int2 import fock_jk
+    bs, o = _pair(oracle_mod, drv, B.water_dimer(), "cc-pvdz")
+    da, db = pack(random_sym_density(bs.nbf, 21)), pack(random_sym_density(bs.nbf, 22))
+    d = np.stack([da, db])
+    f, _ = fock_jk(drv, d, 0.5, 0.8, urohf=True)
+    fo, _ = o.fock(d, 0.5, 0.8, urohf=True)
+    assert np.abs(f - fo).max() < 5e-10  # |D| ~ 3: absolute tolerance scaled
+
+
+def test_multi_fock_rhf(oracle_mod, drv):
+    """nfocks > 1 closed-shell builds (CPHF / Hessian callers, modules/cphf.F90:611)."""
+    from openqp_b200.int2 import fock_jk
+    bs, o = _pair(oracle_mod, drv, B.water(), "cc-pvtz")
+    d = np.stack([pack(random_sym_density(bs.nbf, s, 0.1)) for s in (1, 2, 3)])
+    f, _ = fock_jk(drv, d)
+    fo, _ = o.fock(d)
+    assert np.abs(f - fo).max() < FOCK_TOL
+
+
+def test_scf_energy_golden_through_gpu(oracle_mod, drv):
+    """Config 1: RHF/6-31G(d) water, energy vs examples/HF/H2O_RHF-HF_ENERGY.json within 1e-8 Eh;
+    1e integrals come from the oracle (out of scope of the builder)."""
+    from openqp_b200.int2 import fock_jk
+    ref = golden("reference_energies.json")["h2o_rhf_631gd"]["energy"]
+    mol = B.water()
+    bs, o = _pair(oracle_mod, drv, mol, "6-31g(d)")
+    S, T, V = o.int1e()
+    e, D, F = scf(bs.nbf, S, T + V, mol.nuclear_repulsion(), lambda dp: fock_jk(drv, dp)[0], 5)
+    assert abs(e - ref) < 1e-8
+    e_o, _, _ = scf(bs.nbf, S, T + V, mol.nuclear_repulsion(), lambda dp: o.fock(dp)[0], 5)
+    assert abs(e - e_o) < 1e-10
+    ref_u = golden("reference_energies.json")["h2o_uhf_triplet_631gd"]["energy"]
+    e_u, _, _ = scf(bs.nbf, S, T + V, mol.nuclear_repulsion(), lambda dp: fock_jk(drv, dp, urohf=True)[0], 6, 4)
+    assert abs(e_u - ref_u) < 1e-8
+
+
+def test_td_consumer(oracle_mod, drv):
+    """int2_td_data_t (tdhf_lib.F90:140-224): A+B, A-B and TDA variants."""
+    from openqp_b200.int2 import Int2TdData
+    bs, o = _pair(oracle_mod, drv, B.water(), "cc-pvdz", cutoff=1e-8)
+    rng = np.random.default_rng(5)
+    P = rng.normal(size=(3, bs.nbf, bs.nbf)) * 0.1
+    c = drv.run(Int2TdData(P, int_apb=True, int_amb=True, scale_exchange=0.5))
+    apb, amb, st = o.td(P, 0.5, 1.0, int_apb=True, int_amb=True)
+    assert np.abs(c.apb - apb).max() < 1e-10 and np.abs(c.amb - amb).max() < 1e-10
+    assert c.skipped == st["nschwz"]
+    c = drv.run(Int2TdData(P, tamm_dancoff=True, tamm_dancoff_coulomb=True))
+    apb, amb, st = o.td(P, tamm_dancoff=True, tamm_dancoff_coulomb=True)
+    assert np.abs(c.amb - amb).max() < 1e-10
+    c = drv.run(Int2TdData(P, tamm_dancoff=True))
+    apb, amb, st = o.td(P, tamm_dancoff=True)
+    assert np.abs(c.amb - amb).max() < 1e-10
+
+
+def test_tdhf_golden_through_gpu(oracle_mod, drv):
+    from openqp_b200.int2 import Int2TdData, fock_jk
+    g = golden("reference_energies.json")["h2o_tdhf_631gd"]
+    mol = B.water()
+    bs, o = _pair(oracle_mod, drv, mol, "6-31g(d)")
+    S, T, V = o.int1e()
+
+    def td(P):
+        c = drv.run(Int2TdData(P, int_apb=True, int_amb=True))
+        return c.apb, c.amb
+
+    e, w = rpa_energies(bs, S, T + V, mol.nuclear_repulsion(), 5, lambda dp: fock_jk(drv, dp)[0], td)
+    assert abs(e - g["energy"]) < 1e-8
+    assert np.allclose(w, g["td_energies"], atol=2e-7)
+
+
+def test_mrsf_consumer(oracle_mod, drv):
+    """int2_mrsf_data_t (tdhf_mrsf_lib.F90:218-333): nvec x 7 batched densities (config 5 shape, small)."""
+    from openqp_b200.int2 import Int2MrsfData
+    bs, o = _pair(oracle_mod, drv, B.water_dimer(), "6-31g(d)", cutoff=1e-8)
+    rng = np.random.default_rng(7)
+    d3 = rng.normal(size=(3, 7, bs.nbf, bs.nbf)) * 0.1
+    c = drv.run(Int2MrsfData(d3, scale_exchange=0.5, scale_coulomb=0.5))
+    f3, st = o.mrsf(d3, 0.5, 0.5)
+    assert np.abs(c.f3 - f3).max() < 1e-10
+    assert c.skipped == st["nschwz"]
+
+
+def test_legacy_seam_routec_fock_jk(oracle_mod, drv):
+    """routec_fock_jk (routec_bridge.F90:33-40): by-reference scalars, f returned ready to use, info = 0."""
+    from openqp_b200.int2 import lib
+    bs, o = _pair(oracle_mod, drv, B.water(), "6-31g(d)")
+    d = np.ascontiguousarray(pack(random_sym_density(bs.nbf, 3)))
+    f = np.zeros_like(d)
+    L = lib()
+    L.oqpb_set_default_ctx(drv._h)
+    info, nbf, nf = ctypes.c_int(7), ctypes.c_int(bs.nbf), ctypes.c_int(1)
+    se, sc = ctypes.c_double(1.0), ctypes.c_double(1.0)
+    L.routec_fock_jk(d.ctypes.data_as(ctypes.c_void_p), f.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nbf),
+                     ctypes.byref(nf), ctypes.byref(se), ctypes.byref(sc), ctypes.byref(info))
+    assert info.value == 0
+    fo, _ = o.fock(d)
+    assert np.abs(f - fo[0]).max() < FOCK_TOL
+    nbf_bad = ctypes.c_int(bs.nbf + 1)
+    L.routec_fock_jk(d.ctypes.data_as(ctypes.c_void_p), f.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nbf_bad),
+                     ctypes.byref(nf), ctypes.byref(se), ctypes.byref(sc), ctypes.byref(info))
+    assert info.value != 0  # declines -> native fallback on the Fortran side
+    L.oqpb_set_default_ctx(None)
+
+
+def test_partition_sums_to_full(drv):
+    """Replicated-data split (int2.F90:759-761): partial Focks of 3 ranks add up to the full build."""
+    from openqp_b200.int2 import Int2RhfData
+    bs = B.BasisSet(B.water_dimer(), "cc-pvdz")
+    drv.init(bs)
+    drv.set_screening()
+    d = pack(decaying_density(bs))
+    full = drv.run(Int2RhfData(d))
+    nq = drv.last_stats()["nquartets"]
+    acc, nqs, skipped = np.zeros_like(full.f), 0, 0
+    for r in range(3):
+        drv.set_partition(r, 3)
+        c = drv.run(Int2RhfData(d))
+        acc += c.f
+        nqs += drv.last_stats()["nquartets"]
+        skipped += c.skipped
+    drv.set_partition(0, 1)
+    assert nqs == nq and skipped == full.skipped
+    assert np.abs(acc - full.f).max() < 1e-11
+
+
+def test_full_size_properties_c20h42(drv):
+    """Config 3 (n-C20H42/def2-SVP, 490 bf) -- too large for the serial oracle in seconds, so check
+    size-independent properties: linearity of the build, J/K scale separation, and agreement between the
+    SYM consumer and the GEN (TD, Tamm-Dancoff+Coulomb) consumer on the same symmetric density."""
+    from openqp_b200.int2 import Int2RhfData, Int2TdData
+    mol, bs = B.build("c3")
+    drv.init(bs, 1e-12)
+    drv.set_screening()
+    d1, d2 = decaying_density(bs, 1), decaying_density(bs, 2)
+    f1 = drv.run(Int2RhfData(pack(d1), post=True)).f[0]
+    f2 = drv.run(Int2RhfData(pack(d2), post=True)).f[0]
+    f12 = drv.run(Int2RhfData(pack(d1 + 2 * d2), post=True)).f[0]
+    assert np.abs(f12 - (f1 + 2 * f2)).max() < 1e-9
+    fj = drv.run(Int2RhfData(pack(d1), scale_exchange=0.0, post=True)).f[0]
+    fk = drv.run(Int2RhfData(pack(d1), scale_coulomb=0.0, post=True)).f[0]
+    assert np.abs(fj + fk - f1).max() < 1e-9
+    c = drv.run(Int2TdData(d1[None], tamm_dancoff=True, tamm_dancoff_coulomb=True))
+    # TDA amb = J[P+P^T] - K[P]  (= 2J - K for symmetric P) ;  RHF f = J - K/2
+    assert np.abs(c.amb[0] - 2 * unpack(f1, bs.nbf)).max() < 2e-9
