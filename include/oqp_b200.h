@@ -79,6 +79,8 @@ int oqpb_fock_dev(oqpb_ctx* ctx, int urohf, const double* d_dev, double* f_dev, 
 int oqpb_fock_post_dev(oqpb_ctx* ctx, double* f_dev, int nfocks);
 int oqpb_synchronize(oqpb_ctx* ctx);
 void* oqpb_stream(oqpb_ctx* ctx); /* cudaStream_t the ctx launches on */
+/* launch on the caller's stream instead (e.g. the stream the caller's NCCL communicator is ordered on) */
+int oqpb_set_stream(oqpb_ctx* ctx, void* cuda_stream);
 
 /* int2_td_data_t (tdhf_lib.F90:11-31, update :140-224, parallel_stop symmetrisation :107-109):
  * d2, apb, amb: column-major (nbf, nbf, nvec).  apb is returned symmetrised (apb + apb^T).            */
@@ -100,6 +102,9 @@ double oqpb_last_kernel_ms(oqpb_ctx* ctx); /* CUDA-event time of the ERI/digest 
 /* surviving canonical shell quartets (i>=j, k>=l, (ij)>=(kl), 0-based) of the last build, unordered;
  * returns the count, writes at most maxq quadruples.  Must be enabled before the build.               */
 int oqpb_record_quartets(oqpb_ctx* ctx, int enable);
+/* per-class profiling (serialises launches): out[55][4] = ms, quartets, primitive quartets, model FLOPs of the
+ * builds since the last call; class index = pa*(pa+1)/2+pb over pair classes ss ps pp ds dp dd fs fp fd ff */
+int oqpb_profile(oqpb_ctx* ctx, int enable, double* out);
 long long oqpb_get_quartets(oqpb_ctx* ctx, int* ijkl, long long maxq);
 /* shell-block max|D| of the last build (shlden, int2.F90:999-1047), nshell*nshell                     */
 int oqpb_get_shell_density(oqpb_ctx* ctx, double* dsh, double* max_den);

@@ -113,6 +113,7 @@ double fprim_model(int l1, int l2, int l3, int l4) {
 struct oqpb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   // basis (host copy)
@@ -137,6 +138,8 @@ struct oqpb_ctx {
   long long st_survivors = 0, st_skipped = 0, st_launches = 0;
   double st_flops = 0, st_kernel_ms = 0;
   bool record = false;
+  bool profile = false;
+  double prof[55][4] = {};  // per quartet class: ms, quartets, primitive quartets, model flops
   std::vector<int> rec;  // recorded shell quadruples
   unsigned* h_counts = nullptr;  // pinned
   size_t h_counts_cap = 0;
@@ -751,7 +754,17 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     A.Pgen = S.Pgen; A.Fgen = S.Fgen; A.gen_nmat_total = S.gen_nm; A.gen_ncoul = S.gen_ncoul; A.gen_nvec = S.gen_nvec;
     const ClassEntry& ce = tab[quartet_class(ch.pca, ch.pcb)];
     size_t nb = std::min<size_t>((ch.cand + ce.qpb - 1) / ce.qpb, (size_t)148 * 8);
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (ctx->profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, ctx->stream); }
     CK(ce.launch(A, (int)std::max<size_t>(nb, 1), ctx->stream));
+    if (ctx->profile) {
+      cudaEventRecord(pe1, ctx->stream);
+      cudaEventSynchronize(pe1);
+      float pms = 0;
+      cudaEventElapsedTime(&pms, pe0, pe1);
+      ctx->prof[quartet_class(ch.pca, ch.pcb)][0] += pms;
+      cudaEventDestroy(pe0); cudaEventDestroy(pe1);
+    }
     ctx->st_launches += 2;
     if (ctx->record) {
       unsigned n = 0;
@@ -784,7 +797,12 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     // algorithmic FLOPs: primitive quartets past the int_rys.F90:232 test x F_prim(class)
     // + surviving (de-duplicated) AO integrals x digestion cost per integral
     const Chunk& ch = chunks[c];
-    flops += (double)h_stats[2 * c] * fprim_model(PC_LA[ch.pca], PC_LB[ch.pca], PC_LA[ch.pcb], PC_LB[ch.pcb]);
+    double fl_c = (double)h_stats[2 * c] * fprim_model(PC_LA[ch.pca], PC_LB[ch.pca], PC_LA[ch.pcb], PC_LB[ch.pcb]);
+    if (ctx->profile) {
+      double* pr = ctx->prof[quartet_class(ch.pca, ch.pcb)];
+      pr[1] += n; pr[2] += (double)h_stats[2 * c]; pr[3] += fl_c + (double)h_stats[2 * c + 1] / 8.0 * S.digest_flops_per_int;
+    }
+    flops += fl_c;
     flops += (double)h_stats[2 * c + 1] / 8.0 * S.digest_flops_per_int;
   }
   ctx->st_flops = flops;
@@ -843,7 +861,7 @@ void oqpb_ctx_destroy(oqpb_ctx* ctx) {
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
-  cudaStreamDestroy(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
@@ -995,6 +1013,15 @@ int oqpb_synchronize(oqpb_ctx* ctx) {
   return OQPB_OK;
 }
 void* oqpb_stream(oqpb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int oqpb_set_stream(oqpb_ctx* ctx, void* stream) {
+  if (!ctx) return OQPB_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)stream;
+  ctx->own_stream = false;
+  return OQPB_OK;
+}
 
 int oqpb_fock(oqpb_ctx* ctx, int urohf, const double* d, double* f, int nfocks, double se, double sc, int post,
               long long* nskipped) {
@@ -1120,6 +1147,14 @@ int oqpb_last_stats(oqpb_ctx* ctx, long long* s) {
 }
 double oqpb_last_flops(oqpb_ctx* ctx) { return ctx ? ctx->st_flops : 0.0; }
 double oqpb_last_kernel_ms(oqpb_ctx* ctx) { return ctx ? ctx->st_kernel_ms : 0.0; }
+
+int oqpb_profile(oqpb_ctx* ctx, int enable, double* out /* 55*4 or NULL */) {
+  if (!ctx) return OQPB_ERR_BAD_ARG;
+  if (out) memcpy(out, ctx->prof, sizeof ctx->prof);
+  ctx->profile = enable != 0;
+  memset(ctx->prof, 0, sizeof ctx->prof);
+  return OQPB_OK;
+}
 
 int oqpb_record_quartets(oqpb_ctx* ctx, int enable) {
   if (!ctx) return OQPB_ERR_BAD_ARG;

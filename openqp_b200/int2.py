@@ -141,6 +141,9 @@ class Int2Compute:
     def synchronize(self):
         self._check(lib().oqpb_synchronize(self._h), "oqpb_synchronize")
 
+    def set_stream(self, cuda_stream: int):
+        self._check(lib().oqpb_set_stream(self._h, C.c_void_p(cuda_stream)), "oqpb_set_stream")
+
     def stream(self) -> int:
         return lib().oqpb_stream(self._h)
 
@@ -150,6 +153,19 @@ class Int2Compute:
         lib().oqpb_last_stats(self._h, s)
         return {"nquartets": int(s[0]), "nschwz": int(s[1]), "launches": int(s[3]),
                 "flops": lib().oqpb_last_flops(self._h), "kernel_ms": lib().oqpb_last_kernel_ms(self._h)}
+
+    def profile(self, enable=True):
+        """Enable/disable per-class timing; returns the table accumulated since the previous call."""
+        out = np.zeros((55, 4))
+        lib().oqpb_profile(self._h, C.c_int(1 if enable else 0), _dp(out))
+        names = ["ss", "ps", "pp", "ds", "dp", "dd", "fs", "fp", "fd", "ff"]
+        tab = {}
+        for a in range(10):
+            for b in range(a + 1):
+                r = out[a * (a + 1) // 2 + b]
+                if r[1] > 0:
+                    tab[f"({names[a]}|{names[b]})"] = {"ms": r[0], "quartets": int(r[1]), "prims": int(r[2]), "flops": r[3]}
+        return tab
 
     def record_quartets(self, enable=True):
         lib().oqpb_record_quartets(self._h, C.c_int(1 if enable else 0))
