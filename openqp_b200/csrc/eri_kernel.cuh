@@ -146,7 +146,7 @@ struct ClassCfg {
   static constexpr int BLK = 2 * NCART4;                // ping-pong for the index-wise projection
   static constexpr int QSM0 = (GREG > BLK ? GREG : BLK) + 2 * R + 2;
   static constexpr int QSM = QSM0 | 1;                  // doubles per quartet, odd
-  static constexpr int QPB_T = (288 / TS) > 0 ? (288 / TS) : 1;
+  static constexpr int QPB_T = (64 / TS) > 0 ? (64 / TS) : 1;  // small CTAs: lock-step over few quartets, many CTAs/SM
   static constexpr int QPB_S = (12288 / QSM) > 0 ? (12288 / QSM) : 1;  // <= 96 KB of dynamic smem per CTA
   static constexpr int QPB = QPB_T < QPB_S ? QPB_T : QPB_S;
   static constexpr int NT = ((TS * QPB + 31) / 32) * 32;
@@ -679,22 +679,185 @@ eri_kernel(const EriArgs A) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Register kernel for the small classes (NCART4 <= SMALL_MAX): one thread = one shell quartet, no shared
+// memory, no barriers.  Same arithmetic as eri_kernel (2-D VRR on A and C, HRR to B and D, I += gx gy gz);
+// the finished block is kept in thread-local memory and digested by the same device functions (t=0, ts=1).
+constexpr int SMALL_MAX = 36;
+
 template <int LA, int LB, int LC, int LD>
-cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
+__global__ void __launch_bounds__(128)
+eri_small_kernel(const EriArgs A) {
   using Cfg = ClassCfg<LA, LB, LC, LD>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(eri_kernel<LA, LB, LC, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::SMEM);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
+  constexpr int R = Cfg::R, NA = Cfg::NA, NB = Cfg::NB, NC = Cfg::NC, ND = Cfg::ND, NCART4 = Cfg::NCART4;
+  constexpr int NMAX = Cfg::NMAX, MMAX = Cfg::MMAX, NKL1 = Cfg::NKL1, NIJ1 = Cfg::NIJ1;
+  const unsigned ntasks = *A.ntasks;
+  const ProjTable* PT = A.proj;
+  unsigned long long st_prim = 0, st_ints = 0;
+  for (unsigned ti = blockIdx.x * blockDim.x + threadIdx.x; ti < ntasks; ti += gridDim.x * blockDim.x) {
+    const int2 tk = A.tasks[ti];
+    const PairEntry pb = A.bra[tk.x], pk = A.ket[tk.y];
+    const double* xa = A.xyz + 3 * pb.sa; const double* xb = A.xyz + 3 * pb.sb;
+    const double* xc = A.xyz + 3 * pk.sa; const double* xd = A.xyz + 3 * pk.sb;
+    const double Ax = xa[0], Ay = xa[1], Az = xa[2], Cx = xc[0], Cy = xc[1], Cz = xc[2];
+    const double AB[3] = {Ax - xb[0], Ay - xb[1], Az - xb[2]};
+    const double CD[3] = {Cx - xd[0], Cy - xd[1], Cz - xd[2]};
+    double acc[NCART4];
+#pragma unroll
+    for (int k = 0; k < NCART4; ++k) acc[k] = 0.0;
+    bool any = false;
+    for (int kq = 0; kq < pk.pcnt; ++kq) {
+      const double* pq = A.prim + (size_t)(pk.poff + kq) * PRIM_STRIDE;
+      const double Qx = __ldg(pq), Qy = __ldg(pq + 1), Qz = __ldg(pq + 2), eta = __ldg(pq + 3), Kq = __ldg(pq + 4);
+      for (int kp = 0; kp < pb.pcnt; ++kp) {
+        const double* pp = A.prim + (size_t)(pb.poff + kp) * PRIM_STRIDE;
+        const double Px = __ldg(pp), Py = __ldg(pp + 1), Pz = __ldg(pp + 2), zeta = __ldg(pp + 3), Kp = __ldg(pp + 4);
+        const double ab = zeta + eta;
+        const double pfac = (Kp / zeta) * (Kq / eta);
+        if (pfac * pfac < A.prim_cutoff * ab) continue;  // int_rys.F90:229-232
+        any = true;
+        ++st_prim;
+        const double abinv = 1.0 / ab;
+        const double rho = zeta * eta * abinv;
+        const double PQ[3] = {Px - Qx, Py - Qy, Pz - Qz};
+        const double PA[3] = {Px - Ax, Py - Ay, Pz - Az};
+        const double QC[3] = {Qx - Cx, Qy - Cy, Qz - Cz};
+        const double X = rho * (PQ[0] * PQ[0] + PQ[1] * PQ[1] + PQ[2] * PQ[2]);
+        const double pref = pfac * sqrt(abinv);
+        const double rz = rho / zeta, re = rho / eta, hz = 0.5 / zeta, he = 0.5 / eta;
+#pragma unroll 1
+        for (int r = 0; r < R; ++r) {
+          const double t2 = rys_eval<R>(A, X, r);
+          const double w = rys_eval<R>(A, X, R + r);
+          const double b10 = hz * (1.0 - t2 * rz), b01 = he * (1.0 - t2 * re), b00 = 0.5 * t2 * abinv;
+          double g[3][NIJ1 * NKL1];
+#pragma unroll
+          for (int dir = 0; dir < 3; ++dir) {
+            const double c00 = PA[dir] - t2 * rz * PQ[dir];
+            const double d00 = QC[dir] + t2 * re * PQ[dir];
+            double v[NMAX][MMAX];
+            v[0][0] = dir == 0 ? w * pref : 1.0;
+#pragma unroll
+            for (int n = 1; n < NMAX; ++n) v[n][0] = c00 * v[n - 1][0] + (n >= 2 ? (n - 1) * b10 * v[n >= 2 ? n - 2 : 0][0] : 0.0);
+#pragma unroll
+            for (int m = 1; m < MMAX; ++m) {
+              v[0][m] = d00 * v[0][m - 1] + (m >= 2 ? (m - 1) * b01 * v[0][m >= 2 ? m - 2 : 0] : 0.0);
+#pragma unroll
+              for (int n = 1; n < NMAX; ++n)
+                v[n][m] = d00 * v[n][m - 1] + n * b00 * v[n - 1][m - 1] + (m >= 2 ? (m - 1) * b01 * v[n][m >= 2 ? m - 2 : 0] : 0.0);
+            }
+            // ket HRR then bra HRR
+            double h[NMAX][NKL1];
+#pragma unroll
+            for (int n = 0; n < NMAX; ++n) {
+#pragma unroll
+              for (int c = 0; c <= LC; ++c) h[n][c * (LD + 1)] = v[n][c];
+#pragma unroll
+              for (int d = 1; d <= LD; ++d) {
+#pragma unroll
+                for (int c = 0; c < MMAX - d; ++c) v[n][c] = v[n][c + 1] + CD[dir] * v[n][c];
+#pragma unroll
+                for (int c = 0; c <= LC; ++c) h[n][c * (LD + 1) + d] = v[n][c];
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < NKL1; ++k) {
+#pragma unroll
+              for (int a = 0; a <= LA; ++a) g[dir][(a * (LB + 1)) * NKL1 + k] = h[a][k];
+#pragma unroll
+              for (int b = 1; b <= LB; ++b) {
+#pragma unroll
+                for (int n = 0; n < NMAX - b; ++n) h[n][k] = h[n + 1][k] + AB[dir] * h[n][k];
+#pragma unroll
+                for (int a = 0; a <= LA; ++a) g[dir][(a * (LB + 1) + b) * NKL1 + k] = h[a][k];
+              }
+            }
+          }
+          static_for<0, NCART4>([&](auto I) {
+            constexpr int e = decltype(I)::value;
+            constexpr int id = e % ND, ic = (e / ND) % NC, ib = (e / (ND * NC)) % NB, ia = e / (ND * NC * NB);
+            constexpr int ix = (Cart<LA>::x(ia) * (LB + 1) + Cart<LB>::x(ib)) * NKL1 + Cart<LC>::x(ic) * (LD + 1) + Cart<LD>::x(id);
+            constexpr int iy = (Cart<LA>::y(ia) * (LB + 1) + Cart<LB>::y(ib)) * NKL1 + Cart<LC>::y(ic) * (LD + 1) + Cart<LD>::y(id);
+            constexpr int iz = (Cart<LA>::z(ia) * (LB + 1) + Cart<LB>::z(ib)) * NKL1 + Cart<LC>::z(ic) * (LD + 1) + Cart<LD>::z(id);
+            acc[e] = fma(g[0][ix] * g[1][iy], g[2][iz], acc[e]);
+          });
+        }
+      }
+    }
+    if (!any) {
+      if (A.mode == MODE_SCHWARZ) A.qout[tk.x] = 0.0;
+      if (A.mode == MODE_BLOCK)
+        for (int e = 0; e < PT[0].nout * PT[1].nout * PT[2].nout * PT[3].nout; ++e) A.blockout[e] = 0.0;
+      continue;
+    }
+    // block in thread-local memory; index-wise normalisation / projection, then the shared digestion code
+    double blk0[NCART4], blk1[NCART4];
+#pragma unroll
+    for (int k = 0; k < NCART4; ++k) blk0[k] = acc[k];
+    double* src = blk0;
+    double* dst = blk1;
+    int n0 = NA, n1 = NB, n2 = NC, n3 = ND;
+    if (LD >= 2) { proj_pass(src, dst, n0 * n1 * n2, n3, 1, PT[3], 0, 1); n3 = PT[3].nout; double* tmp = src; src = dst; dst = tmp; }
+    if (LC >= 2) { proj_pass(src, dst, n0 * n1, n2, n3, PT[2], 0, 1); n2 = PT[2].nout; double* tmp = src; src = dst; dst = tmp; }
+    if (LB >= 2) { proj_pass(src, dst, n0, n1, n2 * n3, PT[1], 0, 1); n1 = PT[1].nout; double* tmp = src; src = dst; dst = tmp; }
+    if (LA >= 2) { proj_pass(src, dst, 1, n0, n1 * n2 * n3, PT[0], 0, 1); n0 = PT[0].nout; double* tmp = src; src = dst; dst = tmp; }
+    const int ntot = n0 * n1 * n2 * n3;
+    if (A.mode == MODE_SCHWARZ) {
+      double mx = 0.0;
+      for (int e = 0; e < ntot; ++e) mx = fmax(mx, fabs(src[e]));
+      A.qout[tk.x] = sqrt(mx);
+      continue;
+    }
+    if (A.mode == MODE_BLOCK) {
+      for (int e = 0; e < ntot; ++e) A.blockout[e] = src[e];
+      continue;
+    }
+    float facf = 1.0f;
+    if (pb.sa == pb.sb) facf *= 0.5f;
+    if (pk.sa == pk.sb) facf *= 0.5f;
+    if (pb.sa == pk.sa && pb.sb == pk.sb) facf *= 0.5f;
+    const double fac = (double)facf, cut = A.cutoff;
+    unsigned nz = 0;
+    for (int e = 0; e < ntot; ++e) {
+      double v = src[e];
+      bool z = fabs(v) < cut;
+      nz += !z;
+      src[e] = z ? 0.0 : v * fac;
+    }
+    st_ints += (unsigned long long)nz * (unsigned)(8.0f * facf);
+    const int oa = A.aooff[pb.sa], ob = A.aooff[pb.sb], oc = A.aooff[pk.sa], od = A.aooff[pk.sb];
+    if (A.mode == MODE_SYM) digest_sym(A, src, n0, n1, n2, n3, oa, ob, oc, od, 0, 1);
+    else digest_gen(A, src, n0, n1, n2, n3, oa, ob, oc, od, 0, 1);
   }
-  eri_kernel<LA, LB, LC, LD><<<nblocks, Cfg::NT, Cfg::SMEM, st>>>(args);
-  return cudaGetLastError();
+  if (A.stat) {
+    if (st_prim) atomicAdd(A.stat, st_prim);
+    if (st_ints) atomicAdd(A.stat + 1, st_ints);
+  }
 }
 
 template <int LA, int LB, int LC, int LD>
-int class_qpb() { return ClassCfg<LA, LB, LC, LD>::QPB; }
+cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
+  using Cfg = ClassCfg<LA, LB, LC, LD>;
+  if constexpr (Cfg::NCART4 <= SMALL_MAX) {
+    eri_small_kernel<LA, LB, LC, LD><<<nblocks, 128, 0, st>>>(args);
+    return cudaGetLastError();
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(eri_kernel<LA, LB, LC, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)Cfg::SMEM);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    eri_kernel<LA, LB, LC, LD><<<nblocks, Cfg::NT, Cfg::SMEM, st>>>(args);
+    return cudaGetLastError();
+  }
+}
+
+template <int LA, int LB, int LC, int LD>
+constexpr int class_tasks_per_cta() {
+  return ClassCfg<LA, LB, LC, LD>::NCART4 <= SMALL_MAX ? 128 : ClassCfg<LA, LB, LC, LD>::QPB;
+}
 
 using LaunchFn = cudaError_t (*)(const EriArgs&, int, cudaStream_t);
 struct ClassEntry { LaunchFn launch; int qpb; int nt; size_t smem; };

@@ -753,7 +753,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     A.cj = S.cj; A.ck = S.ck;
     A.Pgen = S.Pgen; A.Fgen = S.Fgen; A.gen_nmat_total = S.gen_nm; A.gen_ncoul = S.gen_ncoul; A.gen_nvec = S.gen_nvec;
     const ClassEntry& ce = tab[quartet_class(ch.pca, ch.pcb)];
-    size_t nb = std::min<size_t>((ch.cand + ce.qpb - 1) / ce.qpb, (size_t)148 * 8);
+    size_t nb = std::min<size_t>((ch.cand + ce.qpb - 1) / ce.qpb, (size_t)148 * 32);
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (ctx->profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, ctx->stream); }
     CK(ce.launch(A, (int)std::max<size_t>(nb, 1), ctx->stream));
