@@ -25,7 +25,8 @@ namespace oqpb {
 
 struct PairEntry {
   int sa, sb;      // shells, am(sa) >= am(sb); equal am: sa is the canonical row shell (sa >= sb)
-  int poff, pcnt;  // primitive-pair records
+  int poff, pcnt;  // primitive-pair records, sorted by |K|/zeta descending
+  double zmin;     // smallest zeta of the pair (lower bound of zeta+eta in the primitive-quartet test)
 };
 
 constexpr int PRIM_STRIDE = 5;  // Px Py Pz zeta K  (K = sqrt(2) pi^{5/4} c_a c_b exp(-ab R^2/zeta), int2_pairs.F90:259)
@@ -150,16 +151,16 @@ struct ClassCfg {
   static constexpr int QPB_S = (12288 / QSM) > 0 ? (12288 / QSM) : 1;  // <= 96 KB of dynamic smem per CTA
   static constexpr int QPB = QPB_T < QPB_S ? QPB_T : QPB_S;
   static constexpr int NT = ((TS * QPB + 31) / 32) * 32;
-  static constexpr size_t SMEM = (size_t)QPB * QSM * sizeof(double) + QPB * 64 * sizeof(int);
+  static constexpr size_t SMEM = (size_t)QPB * QSM * sizeof(double) + QPB * (sizeof(int) * 24 + 64 * sizeof(unsigned short));
 };
 
 struct QInfo {  // 64 ints per quartet in shared memory
   int sa, sb, sc, sd;
   int boff, bcnt, koff, kcnt;
   int oa, ob, oc, od;
-  int valid, nonzero, keep, pad;
+  int valid, nonzero, imax, jmax;
   float fac;
-  int bra_id, ket_id, pad2;
+  int bra_id, ket_id, lcount;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -407,8 +408,9 @@ eri_kernel(const EriArgs A) {
 
   extern __shared__ double smem[];
   QInfo* qinfo = reinterpret_cast<QInfo*>(smem + (size_t)QPB * QSM);
-  __shared__ int s_maxk;
+  __shared__ int s_maxk, s_maxl;
   __shared__ unsigned s_base;
+  constexpr int LCAP = 64;  // primitive-quartet list window
 
   const int tid = threadIdx.x;
   const int q = tid / TS;   // local quartet
@@ -417,6 +419,7 @@ eri_kernel(const EriArgs A) {
   double* qs = smem + (size_t)(team_ok ? q : 0) * QSM;
   double* rw = qs + (QSM - 2 * R - 1);   // roots/weights live at the tail of the quartet region
   QInfo& qi = qinfo[team_ok ? q : 0];
+  unsigned short* plist = reinterpret_cast<unsigned short*>(qinfo + QPB) + (size_t)(team_ok ? q : 0) * LCAP;
 
   // thread's bra component
   const int tab = t / KS, slice = t % KS;
@@ -445,6 +448,7 @@ eri_kernel(const EriArgs A) {
       unsigned ti = base + q;
       qi.valid = ti < ntasks;
       qi.nonzero = 0;
+      qi.imax = qi.jmax = 0;
       if (qi.valid) {
         int2 tk = A.tasks[ti];
         PairEntry pb = A.bra[tk.x], pk = A.ket[tk.y];
@@ -457,13 +461,35 @@ eri_kernel(const EriArgs A) {
         if (pk.sa == pk.sb) f *= 0.5f;
         if ((pb.sa == pk.sa && pb.sb == pk.sb) || (pb.sa == pk.sb && pb.sb == pk.sa)) f *= 0.5f;
         qi.fac = f;
-        atomicMax(&s_maxk, pb.pcnt * pk.pcnt);
+        // primitives are sorted by |K|/zeta: only the leading imax x jmax rectangle can pass the
+        // primitive-quartet test (da db)^2 >= cut * (zeta + eta) >= cut * (zmin_bra + zmin_ket)
+        int imax = 0, jmax = 0;
+        if (pb.pcnt > 0 && pk.pcnt > 0) {
+          const double thr = A.prim_cutoff * (1.0 - 1e-9) * (pb.zmin + pk.zmin);
+          const double* p0 = A.prim + (size_t)pb.poff * PRIM_STRIDE;
+          const double* q0 = A.prim + (size_t)pk.poff * PRIM_STRIDE;
+          const double da0 = __ldg(p0 + 4) / __ldg(p0 + 3), db0 = __ldg(q0 + 4) / __ldg(q0 + 3);
+          while (imax < pb.pcnt) {
+            const double* pp = p0 + (size_t)imax * PRIM_STRIDE;
+            double v = __ldg(pp + 4) / __ldg(pp + 3) * db0;
+            if (v * v < thr) break;
+            ++imax;
+          }
+          while (jmax < pk.pcnt) {
+            const double* pq = q0 + (size_t)jmax * PRIM_STRIDE;
+            double v = __ldg(pq + 4) / __ldg(pq + 3) * da0;
+            if (v * v < thr) break;
+            ++jmax;
+          }
+        }
+        qi.imax = imax; qi.jmax = jmax;
+        atomicMax(&s_maxk, imax * jmax);
       }
     }
     __syncthreads();
     const int maxk = s_maxk;
     const bool valid = team_ok && qi.valid;
-    const int bcnt = valid ? qi.bcnt : 1, nprimq = valid ? qi.bcnt * qi.kcnt : 0;
+    const int imax = valid ? qi.imax : 1, ncand = valid ? qi.imax * qi.jmax : 0;
     double Ax = 0, Ay = 0, Az = 0, Cx = 0, Cy = 0, Cz = 0, ABx = 0, ABy = 0, ABz = 0, CDx = 0, CDy = 0, CDz = 0;
     if (valid) {
       const double* xa = A.xyz + 3 * qi.sa; const double* xb = A.xyz + 3 * qi.sb;
@@ -478,20 +504,44 @@ eri_kernel(const EriArgs A) {
     for (int k = 0; k < Cfg::NACC; ++k) acc[k] = 0.0;
     bool any = false;
 
-    for (int ip = 0; ip < maxk; ++ip) {
-      const bool act = ip < nprimq;
-      // primitive pair records (ket outer, bra inner: int_rys.F90:214-220)
+    for (int w0 = 0; w0 < maxk; w0 += LCAP) {
+      // ---- window scan: compact the primitive quartets that pass the int_rys.F90:229-232 test
+      __syncthreads();  // previous window fully consumed (list, s_maxl)
+      if (team_ok && t == 0) qi.lcount = 0;
+      if (tid == 0) s_maxl = 0;
+      __syncthreads();
+      if (valid) {
+        const int wend = min(w0 + LCAP, ncand);
+        for (int cand = w0 + t; cand < wend; cand += TS) {
+          const int i = cand % imax, j = cand / imax;
+          const double* pp = A.prim + (size_t)(qi.boff + i) * PRIM_STRIDE;
+          const double* pq = A.prim + (size_t)(qi.koff + j) * PRIM_STRIDE;
+          const double z = __ldg(pp + 3), e = __ldg(pq + 3);
+          const double pf = (__ldg(pp + 4) / z) * (__ldg(pq + 4) / e);
+          if (!(pf * pf < A.prim_cutoff * (z + e))) {
+            int pos = atomicAdd(&qi.lcount, 1);
+            plist[pos] = (unsigned short)(j * 128 + i);
+          }
+        }
+      }
+      __syncthreads();
+      if (valid && t == 0 && qi.lcount > 0) atomicMax(&s_maxl, qi.lcount);
+      __syncthreads();
+      const int maxl = s_maxl;
+      const int lcount = valid ? qi.lcount : 0;
+    for (int ip = 0; ip < maxl; ++ip) {
+      const bool act = ip < lcount;
       double Px = 0, Py = 0, Pz = 0, zeta = 1, Kp = 0, Qx = 0, Qy = 0, Qz = 0, eta = 1, Kq = 0;
       if (act) {
-        const double* pp = A.prim + (size_t)(qi.boff + ip % bcnt) * PRIM_STRIDE;
-        const double* pq = A.prim + (size_t)(qi.koff + ip / bcnt) * PRIM_STRIDE;
+        const int code = plist[ip];
+        const double* pp = A.prim + (size_t)(qi.boff + (code & 127)) * PRIM_STRIDE;
+        const double* pq = A.prim + (size_t)(qi.koff + (code >> 7)) * PRIM_STRIDE;
         Px = __ldg(pp); Py = __ldg(pp + 1); Pz = __ldg(pp + 2); zeta = __ldg(pp + 3); Kp = __ldg(pp + 4);
         Qx = __ldg(pq); Qy = __ldg(pq + 1); Qz = __ldg(pq + 2); eta = __ldg(pq + 3); Kq = __ldg(pq + 4);
       }
       const double ab = zeta + eta;
       const double pfac = (Kp / zeta) * (Kq / eta);
-      // primitive-quartet screening, int_rys.F90:229-232
-      const bool keep = act && !(pfac * pfac < A.prim_cutoff * ab);
+      const bool keep = act;
       const double abinv = 1.0 / ab;
       const double rho = zeta * eta * abinv;
       const double PQx = Px - Qx, PQy = Py - Qy, PQz = Pz - Qz;
@@ -584,8 +634,11 @@ eri_kernel(const EriArgs A) {
           else { if (slice == 0) body(std::integral_constant<int, 0>{}); else if (slice == 1) body(std::integral_constant<int, 1>{}); else body(std::integral_constant<int, 2>{}); }
         }
       }
-      __syncthreads();
+      // no barrier here: the next iteration's B1 only writes rw, and B2 (which overwrites the g tables read
+      // above) is behind the barrier that follows B1
     }
+    }
+    __syncthreads();
 
     // ---- block to shared memory (Cartesian, raw), region 0
     if (valid) {
@@ -706,15 +759,24 @@ eri_small_kernel(const EriArgs A) {
 #pragma unroll
     for (int k = 0; k < NCART4; ++k) acc[k] = 0.0;
     bool any = false;
+    // primitives are sorted by |K|/zeta: prune with (da db)^2 >= cut*(zeta+eta) >= cut*(zmin_bra+zmin_ket)
+    const double thr = A.prim_cutoff * (1.0 - 1e-9) * (pb.zmin + pk.zmin);
+    double da0 = 0.0;
+    if (pb.pcnt > 0) { const double* p0 = A.prim + (size_t)pb.poff * PRIM_STRIDE; da0 = __ldg(p0 + 4) / __ldg(p0 + 3); }
     for (int kq = 0; kq < pk.pcnt; ++kq) {
       const double* pq = A.prim + (size_t)(pk.poff + kq) * PRIM_STRIDE;
-      const double Qx = __ldg(pq), Qy = __ldg(pq + 1), Qz = __ldg(pq + 2), eta = __ldg(pq + 3), Kq = __ldg(pq + 4);
+      const double eta = __ldg(pq + 3), Kq = __ldg(pq + 4);
+      const double db = Kq / eta;
+      if ((da0 * db) * (da0 * db) < thr) break;
+      const double Qx = __ldg(pq), Qy = __ldg(pq + 1), Qz = __ldg(pq + 2);
       for (int kp = 0; kp < pb.pcnt; ++kp) {
         const double* pp = A.prim + (size_t)(pb.poff + kp) * PRIM_STRIDE;
-        const double Px = __ldg(pp), Py = __ldg(pp + 1), Pz = __ldg(pp + 2), zeta = __ldg(pp + 3), Kp = __ldg(pp + 4);
+        const double zeta = __ldg(pp + 3), Kp = __ldg(pp + 4);
+        const double pfac = (Kp / zeta) * db;
+        if (pfac * pfac < thr) break;
         const double ab = zeta + eta;
-        const double pfac = (Kp / zeta) * (Kq / eta);
         if (pfac * pfac < A.prim_cutoff * ab) continue;  // int_rys.F90:229-232
+        const double Px = __ldg(pp), Py = __ldg(pp + 1), Pz = __ldg(pp + 2);
         any = true;
         ++st_prim;
         const double abinv = 1.0 / ab;

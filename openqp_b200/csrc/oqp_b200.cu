@@ -162,7 +162,7 @@ template <bool FILL>
 __global__ void k_pairs(int nshell, long npairs, const int* __restrict__ am, const int* __restrict__ ncontr,
                         const int* __restrict__ goff, const double* __restrict__ ex, const double* __restrict__ cc,
                         const double* __restrict__ xyz, double exponent_cutoff, double quartet_cutoff,
-                        int* __restrict__ cnt, const PairEntry* __restrict__ ent, double* __restrict__ prim, long nent) {
+                        int* __restrict__ cnt, PairEntry* __restrict__ ent, double* __restrict__ prim, long nent) {
   long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
   int i, j, poff = 0;
   if (FILL) {
@@ -207,7 +207,27 @@ __global__ void k_pairs(int nshell, long npairs, const int* __restrict__ am, con
       }
       ++n;
     }
-  if (!FILL) cnt[id] = n;
+  if (!FILL) {
+    cnt[id] = n;
+  } else {
+    // sort the pair's primitives by |K|/zeta descending (lets the kernels prune the primitive-quartet loops)
+    // and record the smallest zeta
+    double* o = prim + (size_t)poff * PRIM_STRIDE;
+    double zmin = 1e300;
+    for (int a = 0; a < n; ++a) zmin = fmin(zmin, o[a * PRIM_STRIDE + 3]);
+    for (int a = 1; a < n; ++a) {
+      double rec[PRIM_STRIDE];
+      for (int k = 0; k < PRIM_STRIDE; ++k) rec[k] = o[a * PRIM_STRIDE + k];
+      const double key = fabs(rec[4] / rec[3]);
+      int b = a - 1;
+      while (b >= 0 && fabs(o[b * PRIM_STRIDE + 4] / o[b * PRIM_STRIDE + 3]) < key) {
+        for (int k = 0; k < PRIM_STRIDE; ++k) o[(b + 1) * PRIM_STRIDE + k] = o[b * PRIM_STRIDE + k];
+        --b;
+      }
+      for (int k = 0; k < PRIM_STRIDE; ++k) o[(b + 1) * PRIM_STRIDE + k] = rec[k];
+    }
+    ent[id].zmin = n > 0 ? zmin : 0.0;
+  }
 }
 
 __global__ void k_expand_packed(const double* __restrict__ dp, double* __restrict__ dsq, int nbf) {
@@ -503,6 +523,7 @@ int build_pairtable(oqpb_ctx* ctx, const Cutoffs& c, PairTable& T, const std::ve
       if (ctx->am[i] >= ctx->am[j]) { e.sa = i; e.sb = j; } else { e.sa = j; e.sb = i; }
       e.poff = (int)poff;
       e.pcnt = cnt[id];
+      e.zmin = 0.0;
       poff += cnt[id];
       T.ent.push_back(e);
       T.canon.push_back(id);
