@@ -737,10 +737,17 @@ eri_kernel(const EriArgs A) {
 // memory, no barriers.  Same arithmetic as eri_kernel (2-D VRR on A and C, HRR to B and D, I += gx gy gz);
 // the finished block is kept in thread-local memory and digested by the same device functions (t=0, ts=1).
 constexpr int SMALL_MAX = 36;
+// Medium classes (SMALL_MAX < NCART4 <= MEDIUM_MAX): same one-thread-per-quartet kernel, but the finished
+// gx/gy/gz tables of a root live in shared memory (column per thread, [entry][thread]: conflict-free) so the
+// registers are left to the NCART4 accumulators.
+constexpr int MEDIUM_MAX = 100;
+constexpr int SMALL_NT = 128, MEDIUM_NT = 64;
 
-template <int LA, int LB, int LC, int LD>
-__global__ void __launch_bounds__(128)
+template <int LA, int LB, int LC, int LD, bool GS>
+__global__ void __launch_bounds__(GS ? MEDIUM_NT : SMALL_NT)
 eri_small_kernel(const EriArgs A) {
+  constexpr int NTH = GS ? MEDIUM_NT : SMALL_NT;
+  extern __shared__ double gsm[];
   using Cfg = ClassCfg<LA, LB, LC, LD>;
   constexpr int R = Cfg::R, NA = Cfg::NA, NB = Cfg::NB, NC = Cfg::NC, ND = Cfg::ND, NCART4 = Cfg::NCART4;
   constexpr int NMAX = Cfg::NMAX, MMAX = Cfg::MMAX, NKL1 = Cfg::NKL1, NIJ1 = Cfg::NIJ1;
@@ -792,7 +799,13 @@ eri_small_kernel(const EriArgs A) {
           const double t2 = rys_eval<R>(A, X, r);
           const double w = rys_eval<R>(A, X, R + r);
           const double b10 = hz * (1.0 - t2 * rz), b01 = he * (1.0 - t2 * re), b00 = 0.5 * t2 * abinv;
-          double g[3][NIJ1 * NKL1];
+          constexpr int G3 = NIJ1 * NKL1;
+          double g[GS ? 1 : 3][GS ? 1 : G3];
+          double* gcol = gsm + threadIdx.x;
+          auto GSET = [&](int dir, int idx, double val) {
+            if constexpr (GS) gcol[(dir * G3 + idx) * NTH] = val;
+            else g[dir][idx] = val;
+          };
 #pragma unroll
           for (int dir = 0; dir < 3; ++dir) {
             const double c00 = PA[dir] - t2 * rz * PQ[dir];
@@ -825,13 +838,13 @@ eri_small_kernel(const EriArgs A) {
 #pragma unroll
             for (int k = 0; k < NKL1; ++k) {
 #pragma unroll
-              for (int a = 0; a <= LA; ++a) g[dir][(a * (LB + 1)) * NKL1 + k] = h[a][k];
+              for (int a = 0; a <= LA; ++a) GSET(dir, (a * (LB + 1)) * NKL1 + k, h[a][k]);
 #pragma unroll
               for (int b = 1; b <= LB; ++b) {
 #pragma unroll
                 for (int n = 0; n < NMAX - b; ++n) h[n][k] = h[n + 1][k] + AB[dir] * h[n][k];
 #pragma unroll
-                for (int a = 0; a <= LA; ++a) g[dir][(a * (LB + 1) + b) * NKL1 + k] = h[a][k];
+                for (int a = 0; a <= LA; ++a) GSET(dir, (a * (LB + 1) + b) * NKL1 + k, h[a][k]);
               }
             }
           }
@@ -841,7 +854,8 @@ eri_small_kernel(const EriArgs A) {
             constexpr int ix = (Cart<LA>::x(ia) * (LB + 1) + Cart<LB>::x(ib)) * NKL1 + Cart<LC>::x(ic) * (LD + 1) + Cart<LD>::x(id);
             constexpr int iy = (Cart<LA>::y(ia) * (LB + 1) + Cart<LB>::y(ib)) * NKL1 + Cart<LC>::y(ic) * (LD + 1) + Cart<LD>::y(id);
             constexpr int iz = (Cart<LA>::z(ia) * (LB + 1) + Cart<LB>::z(ib)) * NKL1 + Cart<LC>::z(ic) * (LD + 1) + Cart<LD>::z(id);
-            acc[e] = fma(g[0][ix] * g[1][iy], g[2][iz], acc[e]);
+            if constexpr (GS) acc[e] = fma(gcol[ix * NTH] * gcol[(G3 + iy) * NTH], gcol[(2 * G3 + iz) * NTH], acc[e]);
+            else acc[e] = fma(g[0][ix] * g[1][iy], g[2][iz], acc[e]);
           });
         }
       }
@@ -901,7 +915,18 @@ template <int LA, int LB, int LC, int LD>
 cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
   using Cfg = ClassCfg<LA, LB, LC, LD>;
   if constexpr (Cfg::NCART4 <= SMALL_MAX) {
-    eri_small_kernel<LA, LB, LC, LD><<<nblocks, 128, 0, st>>>(args);
+    eri_small_kernel<LA, LB, LC, LD, false><<<nblocks, SMALL_NT, 0, st>>>(args);
+    return cudaGetLastError();
+  } else if constexpr (Cfg::NCART4 <= MEDIUM_MAX) {
+    constexpr size_t smem = (size_t)3 * Cfg::NIJ1 * Cfg::NKL1 * MEDIUM_NT * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(eri_small_kernel<LA, LB, LC, LD, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    eri_small_kernel<LA, LB, LC, LD, true><<<nblocks, MEDIUM_NT, smem, st>>>(args);
     return cudaGetLastError();
   } else {
     static bool attr_set = false;
@@ -918,7 +943,7 @@ cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
 
 template <int LA, int LB, int LC, int LD>
 constexpr int class_tasks_per_cta() {
-  return ClassCfg<LA, LB, LC, LD>::NCART4 <= SMALL_MAX ? 128 : ClassCfg<LA, LB, LC, LD>::QPB;
+  return ClassCfg<LA, LB, LC, LD>::NCART4 <= SMALL_MAX ? SMALL_NT : (ClassCfg<LA, LB, LC, LD>::NCART4 <= MEDIUM_MAX ? MEDIUM_NT : ClassCfg<LA, LB, LC, LD>::QPB);
 }
 
 using LaunchFn = cudaError_t (*)(const EriArgs&, int, cudaStream_t);
