@@ -29,7 +29,9 @@ struct PairEntry {
   double zmin;     // smallest zeta of the pair (lower bound of zeta+eta in the primitive-quartet test)
 };
 
-constexpr int PRIM_STRIDE = 5;  // Px Py Pz zeta K  (K = sqrt(2) pi^{5/4} c_a c_b exp(-ab R^2/zeta), int2_pairs.F90:259)
+// primitive pair record: Px Py Pz zeta da zinv, da = K/zeta with K = sqrt(2) pi^{5/4} c_a c_b exp(-ab R^2/zeta)
+// (int2_pairs.F90:259, int_rys.F90:216); records of a pair are sorted by |da| descending
+constexpr int PRIM_STRIDE = 6;
 
 constexpr int MAX_PROJ_TERMS = 6;
 struct ProjTable {  // output row -> sparse list over my internal Cartesian order (normalisation folded in)
@@ -468,16 +470,16 @@ eri_kernel(const EriArgs A) {
           const double thr = A.prim_cutoff * (1.0 - 1e-9) * (pb.zmin + pk.zmin);
           const double* p0 = A.prim + (size_t)pb.poff * PRIM_STRIDE;
           const double* q0 = A.prim + (size_t)pk.poff * PRIM_STRIDE;
-          const double da0 = __ldg(p0 + 4) / __ldg(p0 + 3), db0 = __ldg(q0 + 4) / __ldg(q0 + 3);
+          const double da0 = __ldg(p0 + 4), db0 = __ldg(q0 + 4);
           while (imax < pb.pcnt) {
             const double* pp = p0 + (size_t)imax * PRIM_STRIDE;
-            double v = __ldg(pp + 4) / __ldg(pp + 3) * db0;
+            double v = __ldg(pp + 4) * db0;
             if (v * v < thr) break;
             ++imax;
           }
           while (jmax < pk.pcnt) {
             const double* pq = q0 + (size_t)jmax * PRIM_STRIDE;
-            double v = __ldg(pq + 4) / __ldg(pq + 3) * da0;
+            double v = __ldg(pq + 4) * da0;
             if (v * v < thr) break;
             ++jmax;
           }
@@ -517,7 +519,7 @@ eri_kernel(const EriArgs A) {
           const double* pp = A.prim + (size_t)(qi.boff + i) * PRIM_STRIDE;
           const double* pq = A.prim + (size_t)(qi.koff + j) * PRIM_STRIDE;
           const double z = __ldg(pp + 3), e = __ldg(pq + 3);
-          const double pf = (__ldg(pp + 4) / z) * (__ldg(pq + 4) / e);
+          const double pf = __ldg(pp + 4) * __ldg(pq + 4);
           if (!(pf * pf < A.prim_cutoff * (z + e))) {
             int pos = atomicAdd(&qi.lcount, 1);
             plist[pos] = (unsigned short)(j * 128 + i);
@@ -531,16 +533,16 @@ eri_kernel(const EriArgs A) {
       const int lcount = valid ? qi.lcount : 0;
     for (int ip = 0; ip < maxl; ++ip) {
       const bool act = ip < lcount;
-      double Px = 0, Py = 0, Pz = 0, zeta = 1, Kp = 0, Qx = 0, Qy = 0, Qz = 0, eta = 1, Kq = 0;
+      double Px = 0, Py = 0, Pz = 0, zeta = 1, Kp = 0, Qx = 0, Qy = 0, Qz = 0, eta = 1, Kq = 0, zinv = 1, einv = 1;
       if (act) {
         const int code = plist[ip];
         const double* pp = A.prim + (size_t)(qi.boff + (code & 127)) * PRIM_STRIDE;
         const double* pq = A.prim + (size_t)(qi.koff + (code >> 7)) * PRIM_STRIDE;
-        Px = __ldg(pp); Py = __ldg(pp + 1); Pz = __ldg(pp + 2); zeta = __ldg(pp + 3); Kp = __ldg(pp + 4);
-        Qx = __ldg(pq); Qy = __ldg(pq + 1); Qz = __ldg(pq + 2); eta = __ldg(pq + 3); Kq = __ldg(pq + 4);
+        Px = __ldg(pp); Py = __ldg(pp + 1); Pz = __ldg(pp + 2); zeta = __ldg(pp + 3); Kp = __ldg(pp + 4); zinv = __ldg(pp + 5);
+        Qx = __ldg(pq); Qy = __ldg(pq + 1); Qz = __ldg(pq + 2); eta = __ldg(pq + 3); Kq = __ldg(pq + 4); einv = __ldg(pq + 5);
       }
       const double ab = zeta + eta;
-      const double pfac = (Kp / zeta) * (Kq / eta);
+      const double pfac = Kp * Kq;
       const bool keep = act;
       const double abinv = 1.0 / ab;
       const double rho = zeta * eta * abinv;
@@ -563,10 +565,10 @@ eri_kernel(const EriArgs A) {
           const double ABd = dir == 0 ? ABx : (dir == 1 ? ABy : ABz);
           const double CDd = dir == 0 ? CDx : (dir == 1 ? CDy : CDz);
           const double t2r = t2 * rho;
-          const double c00 = PAd - t2r / zeta * PQd;
-          const double d00 = QCd + t2r / eta * PQd;
-          const double b10 = 0.5 / zeta * (1.0 - t2r / zeta);
-          const double b01 = 0.5 / eta * (1.0 - t2r / eta);
+          const double c00 = PAd - t2r * zinv * PQd;
+          const double d00 = QCd + t2r * einv * PQd;
+          const double b10 = 0.5 * zinv * (1.0 - t2r * zinv);
+          const double b01 = 0.5 * einv * (1.0 - t2r * einv);
           const double b00 = 0.5 * t2 * abinv;
           double* S1 = qs + (size_t)task * GSTR;   // [n][m], m fastest
           double* S2 = S1 + G1;                    // [n][c][d]
@@ -769,17 +771,16 @@ eri_small_kernel(const EriArgs A) {
     // primitives are sorted by |K|/zeta: prune with (da db)^2 >= cut*(zeta+eta) >= cut*(zmin_bra+zmin_ket)
     const double thr = A.prim_cutoff * (1.0 - 1e-9) * (pb.zmin + pk.zmin);
     double da0 = 0.0;
-    if (pb.pcnt > 0) { const double* p0 = A.prim + (size_t)pb.poff * PRIM_STRIDE; da0 = __ldg(p0 + 4) / __ldg(p0 + 3); }
+    if (pb.pcnt > 0) { const double* p0 = A.prim + (size_t)pb.poff * PRIM_STRIDE; da0 = __ldg(p0 + 4); }
     for (int kq = 0; kq < pk.pcnt; ++kq) {
       const double* pq = A.prim + (size_t)(pk.poff + kq) * PRIM_STRIDE;
-      const double eta = __ldg(pq + 3), Kq = __ldg(pq + 4);
-      const double db = Kq / eta;
+      const double eta = __ldg(pq + 3), db = __ldg(pq + 4), einv = __ldg(pq + 5);
       if ((da0 * db) * (da0 * db) < thr) break;
       const double Qx = __ldg(pq), Qy = __ldg(pq + 1), Qz = __ldg(pq + 2);
       for (int kp = 0; kp < pb.pcnt; ++kp) {
         const double* pp = A.prim + (size_t)(pb.poff + kp) * PRIM_STRIDE;
-        const double zeta = __ldg(pp + 3), Kp = __ldg(pp + 4);
-        const double pfac = (Kp / zeta) * db;
+        const double zeta = __ldg(pp + 3), zinv = __ldg(pp + 5);
+        const double pfac = __ldg(pp + 4) * db;
         if (pfac * pfac < thr) break;
         const double ab = zeta + eta;
         if (pfac * pfac < A.prim_cutoff * ab) continue;  // int_rys.F90:229-232
@@ -793,7 +794,7 @@ eri_small_kernel(const EriArgs A) {
         const double QC[3] = {Qx - Cx, Qy - Cy, Qz - Cz};
         const double X = rho * (PQ[0] * PQ[0] + PQ[1] * PQ[1] + PQ[2] * PQ[2]);
         const double pref = pfac * sqrt(abinv);
-        const double rz = rho / zeta, re = rho / eta, hz = 0.5 / zeta, he = 0.5 / eta;
+        const double rz = rho * zinv, re = rho * einv, hz = 0.5 * zinv, he = 0.5 * einv;
 #pragma unroll 1
         for (int r = 0; r < R; ++r) {
           const double t2 = rys_eval<R>(A, X, r);
@@ -911,6 +912,327 @@ eri_small_kernel(const EriArgs A) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Group kernel for the large classes: a quartet is owned by an aligned group of G lanes of ONE warp
+// (G = 4, 8, 16 or 32), a warp works on 32/G quartets at once, and every phase boundary is a __syncwarp():
+// no CTA barrier anywhere, warps fetch their own work.  Each lane owns NVL = ceil(NA*NB/G) bra Cartesian
+// component pairs ("virtual lanes") with all NC*ND ket components in registers.  Phases per primitive quartet
+// as in eri_kernel: B1 roots (2R tasks over the G lanes), B2 2-D recurrences (3R tasks), B3 assembly.
+template <int LA, int LB, int LC, int LD>
+struct GroupCfg {
+  using C = ClassCfg<LA, LB, LC, LD>;
+  static constexpr int VL = C::NA * C::NB;
+  static constexpr int NKET = C::NKET;
+  static constexpr int acc_for(int g) { return ((VL + g - 1) / g) * NKET; }
+  static constexpr int LIMIT = 40;      // accumulators per lane for G < 32
+  static constexpr int LIMIT32 = 72;    // ... and for full-warp groups
+  static constexpr bool OK = (C::KS == 1) && acc_for(32) <= LIMIT32;
+  static constexpr int G = acc_for(4) <= LIMIT ? 4 : (acc_for(8) <= LIMIT ? 8 : (acc_for(16) <= LIMIT ? 16 : 32));
+  static constexpr int NVL = (VL + G - 1) / G;
+  static constexpr int QPW = 32 / G;
+  static constexpr int QBYTES = C::QSM * 8 + 96 + 128;  // block/g region + QInfo + primitive list
+  static constexpr int WPC = (2 * QPW * QBYTES <= 64 * 1024) ? 2 : 1;
+  static constexpr int NT = 32 * WPC;
+  static constexpr size_t SMEM = (size_t)WPC * QPW * QBYTES;
+};
+
+template <int LA, int LB, int LC, int LD>
+__global__ void __launch_bounds__(GroupCfg<LA, LB, LC, LD>::NT)
+eri_group_kernel(const EriArgs A) {
+  using Cfg = ClassCfg<LA, LB, LC, LD>;
+  using GC = GroupCfg<LA, LB, LC, LD>;
+  constexpr int R = Cfg::R, NA = Cfg::NA, NB = Cfg::NB, NC = Cfg::NC, ND = Cfg::ND, NKET = Cfg::NKET;
+  constexpr int NMAX = Cfg::NMAX, MMAX = Cfg::MMAX, NKL1 = Cfg::NKL1;
+  constexpr int G1 = Cfg::G1, G2 = Cfg::G2, GSTR = Cfg::GSTR, QSM = Cfg::QSM;
+  constexpr int G = GC::G, NVL = GC::NVL, QPW = GC::QPW, VL = GC::VL;
+  constexpr int LCAP = 64;
+  constexpr unsigned FULL = 0xffffffffu;
+
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = lane / G, t = lane % G;
+  const int qslot = w * QPW + g;
+  double* qs = smem + (size_t)qslot * QSM;
+  double* rw = qs + (QSM - 2 * R - 2);  // 2R roots/weights + abinv + prefactor
+  char* tail = reinterpret_cast<char*>(smem + (size_t)GC::WPC * QPW * QSM);
+  QInfo& qi = *reinterpret_cast<QInfo*>(tail + (size_t)qslot * 96);
+  unsigned short* plist = reinterpret_cast<unsigned short*>(tail + (size_t)GC::WPC * QPW * 96) + (size_t)qslot * LCAP;
+
+  // virtual lanes of this thread
+  int obx[NVL], oby[NVL], obz[NVL];
+#pragma unroll
+  for (int j = 0; j < NVL; ++j) {
+    int vt = t + G * j;
+    int ia = (vt < VL ? vt : 0) / NB, ib = (vt < VL ? vt : 0) % NB;
+    int ax, ay, az, bx, by, bz;
+    cart_xyz_rt(LA, ia, ax, ay, az);
+    cart_xyz_rt(LB, ib, bx, by, bz);
+    obx[j] = (ax * (LB + 1) + bx) * NKL1; oby[j] = (ay * (LB + 1) + by) * NKL1; obz[j] = (az * (LB + 1) + bz) * NKL1;
+  }
+  const unsigned ntasks = *A.ntasks;
+  const ProjTable* PT = A.proj;
+  unsigned long long st_prim = 0, st_ints = 0;
+
+  for (;;) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(A.counter, (unsigned)QPW);
+    base = __shfl_sync(FULL, base, 0);
+    if (base >= ntasks) break;
+    __syncwarp();
+    if (t == 0) {
+      unsigned ti = base + g;
+      qi.valid = ti < ntasks;
+      qi.nonzero = 0;
+      qi.imax = qi.jmax = 0;
+      qi.lcount = 0;
+      if (qi.valid) {
+        int2 tk = A.tasks[ti];
+        PairEntry pb = A.bra[tk.x], pk = A.ket[tk.y];
+        qi.sa = pb.sa; qi.sb = pb.sb; qi.sc = pk.sa; qi.sd = pk.sb;
+        qi.boff = pb.poff; qi.bcnt = pb.pcnt; qi.koff = pk.poff; qi.kcnt = pk.pcnt;
+        qi.oa = A.aooff[pb.sa]; qi.ob = A.aooff[pb.sb]; qi.oc = A.aooff[pk.sa]; qi.od = A.aooff[pk.sb];
+        qi.bra_id = tk.x; qi.ket_id = tk.y;
+        float f = 1.0f;
+        if (pb.sa == pb.sb) f *= 0.5f;
+        if (pk.sa == pk.sb) f *= 0.5f;
+        if (pb.sa == pk.sa && pb.sb == pk.sb) f *= 0.5f;
+        qi.fac = f;
+        int imax = 0, jmax = 0;
+        if (pb.pcnt > 0 && pk.pcnt > 0) {
+          const double thr = A.prim_cutoff * (1.0 - 1e-9) * (pb.zmin + pk.zmin);
+          const double* p0 = A.prim + (size_t)pb.poff * PRIM_STRIDE;
+          const double* q0 = A.prim + (size_t)pk.poff * PRIM_STRIDE;
+          const double da0 = __ldg(p0 + 4), db0 = __ldg(q0 + 4);
+          while (imax < pb.pcnt) { double v = __ldg(p0 + (size_t)imax * PRIM_STRIDE + 4) * db0; if (v * v < thr) break; ++imax; }
+          while (jmax < pk.pcnt) { double v = __ldg(q0 + (size_t)jmax * PRIM_STRIDE + 4) * da0; if (v * v < thr) break; ++jmax; }
+        }
+        qi.imax = imax; qi.jmax = jmax;
+      }
+    }
+    __syncwarp();
+    const bool valid = qi.valid;
+    const int imax = valid ? max(qi.imax, 1) : 1, ncand = valid ? qi.imax * qi.jmax : 0;
+    const int maxk = __reduce_max_sync(FULL, ncand);
+    double Ax = 0, Ay = 0, Az = 0, Cx = 0, Cy = 0, Cz = 0, ABx = 0, ABy = 0, ABz = 0, CDx = 0, CDy = 0, CDz = 0;
+    if (valid) {
+      const double* xa = A.xyz + 3 * qi.sa; const double* xb = A.xyz + 3 * qi.sb;
+      const double* xc = A.xyz + 3 * qi.sc; const double* xd = A.xyz + 3 * qi.sd;
+      Ax = xa[0]; Ay = xa[1]; Az = xa[2]; Cx = xc[0]; Cy = xc[1]; Cz = xc[2];
+      ABx = Ax - xb[0]; ABy = Ay - xb[1]; ABz = Az - xb[2];
+      CDx = Cx - xd[0]; CDy = Cy - xd[1]; CDz = Cz - xd[2];
+    }
+    double acc[NVL][NKET];
+#pragma unroll
+    for (int j = 0; j < NVL; ++j)
+#pragma unroll
+      for (int k = 0; k < NKET; ++k) acc[j][k] = 0.0;
+    bool any = false;
+
+    for (int w0 = 0; w0 < maxk; w0 += LCAP) {
+      __syncwarp();
+      if (t == 0) qi.lcount = 0;
+      __syncwarp();
+      if (valid) {
+        const int wend = min(w0 + LCAP, ncand);
+        for (int cand = w0 + t; cand < wend; cand += G) {
+          const int i = cand % imax, j = cand / imax;
+          const double* pp = A.prim + (size_t)(qi.boff + i) * PRIM_STRIDE;
+          const double* pq = A.prim + (size_t)(qi.koff + j) * PRIM_STRIDE;
+          const double pf = __ldg(pp + 4) * __ldg(pq + 4);
+          if (!(pf * pf < A.prim_cutoff * (__ldg(pp + 3) + __ldg(pq + 3)))) {
+            int pos = atomicAdd(&qi.lcount, 1);
+            plist[pos] = (unsigned short)(j * 128 + i);
+          }
+        }
+      }
+      __syncwarp();
+      const int lcount = valid ? qi.lcount : 0;
+      const int maxl = __reduce_max_sync(FULL, lcount);
+      for (int ip = 0; ip < maxl; ++ip) {
+        const bool keep = ip < lcount;
+        double Px = 0, Py = 0, Pz = 0, zeta = 1, Kp = 0, Qx = 0, Qy = 0, Qz = 0, eta = 1, Kq = 0, zinv = 1, einv = 1;
+        if (keep) {
+          const int code = plist[ip];
+          const double* pp = A.prim + (size_t)(qi.boff + (code & 127)) * PRIM_STRIDE;
+          const double* pq = A.prim + (size_t)(qi.koff + (code >> 7)) * PRIM_STRIDE;
+          Px = __ldg(pp); Py = __ldg(pp + 1); Pz = __ldg(pp + 2); zeta = __ldg(pp + 3); Kp = __ldg(pp + 4); zinv = __ldg(pp + 5);
+          Qx = __ldg(pq); Qy = __ldg(pq + 1); Qz = __ldg(pq + 2); eta = __ldg(pq + 3); Kq = __ldg(pq + 4); einv = __ldg(pq + 5);
+        }
+        const double PQx = Px - Qx, PQy = Py - Qy, PQz = Pz - Qz;
+        // ---- B1: lane 0 of the group prepares the primitive scalars, 2R lanes evaluate roots and weights
+        if (keep) {
+          const double abinv = 1.0 / (zeta + eta);
+          const double rho = zeta * eta * abinv;
+          const double X = rho * (PQx * PQx + PQy * PQy + PQz * PQz);
+          if (t == 0) { rw[2 * R] = abinv; rw[2 * R + 1] = Kp * Kq * sqrt(abinv); }
+          for (int f = t; f < 2 * R; f += G) rw[f] = rys_eval<R>(A, X, f);
+        }
+        __syncwarp();
+        // ---- B2: 2-D recurrences, (root, direction) tasks over the G lanes
+        if (keep) {
+          const double abinv = rw[2 * R], pref = rw[2 * R + 1];
+          const double rho = zeta * eta * abinv;
+          for (int task = t; task < 3 * R; task += G) {
+            const int r = task / 3, dir = task % 3;
+            const double t2 = rw[r];
+            const double PAd = dir == 0 ? Px - Ax : (dir == 1 ? Py - Ay : Pz - Az);
+            const double QCd = dir == 0 ? Qx - Cx : (dir == 1 ? Qy - Cy : Qz - Cz);
+            const double PQd = dir == 0 ? PQx : (dir == 1 ? PQy : PQz);
+            const double ABd = dir == 0 ? ABx : (dir == 1 ? ABy : ABz);
+            const double CDd = dir == 0 ? CDx : (dir == 1 ? CDy : CDz);
+            const double t2r = t2 * rho;
+            const double c00 = PAd - t2r * zinv * PQd;
+            const double d00 = QCd + t2r * einv * PQd;
+            const double b10 = 0.5 * zinv * (1.0 - t2r * zinv);
+            const double b01 = 0.5 * einv * (1.0 - t2r * einv);
+            const double b00 = 0.5 * t2 * abinv;
+            double* S1 = qs + (size_t)task * GSTR;
+            double* S2 = S1 + G1;
+            double* S3 = S2 + G2;
+            S1[0] = dir == 0 ? rw[R + r] * pref : 1.0;
+            if (NMAX > 1) S1[MMAX] = c00 * S1[0];
+            for (int n = 1; n < NMAX - 1; ++n) S1[(n + 1) * MMAX] = c00 * S1[n * MMAX] + n * b10 * S1[(n - 1) * MMAX];
+            for (int m = 0; m < MMAX - 1; ++m) {
+              double v0 = d00 * S1[m];
+              if (m > 0) v0 += m * b01 * S1[m - 1];
+              S1[m + 1] = v0;
+              for (int n = 1; n < NMAX; ++n) {
+                double v = d00 * S1[n * MMAX + m] + n * b00 * S1[(n - 1) * MMAX + m];
+                if (m > 0) v += m * b01 * S1[n * MMAX + m - 1];
+                S1[n * MMAX + m + 1] = v;
+              }
+            }
+            for (int n = 0; n < NMAX; ++n) {
+              double* wv = S1 + n * MMAX;
+              for (int c = 0; c <= LC; ++c) S2[(n * (LC + 1) + c) * (LD + 1)] = wv[c];
+              for (int d = 1; d <= LD; ++d) {
+                for (int c = 0; c < MMAX - d; ++c) wv[c] = wv[c + 1] + CDd * wv[c];
+                for (int c = 0; c <= LC; ++c) S2[(n * (LC + 1) + c) * (LD + 1) + d] = wv[c];
+              }
+            }
+            for (int k = 0; k < NKL1; ++k) {
+              for (int a = 0; a <= LA; ++a) S3[(a * (LB + 1)) * NKL1 + k] = S2[a * NKL1 + k];
+              for (int b = 1; b <= LB; ++b) {
+                for (int n = 0; n < NMAX - b; ++n) S2[n * NKL1 + k] = S2[(n + 1) * NKL1 + k] + ABd * S2[n * NKL1 + k];
+                for (int a = 0; a <= LA; ++a) S3[(a * (LB + 1) + b) * NKL1 + k] = S2[a * NKL1 + k];
+              }
+            }
+          }
+        }
+        __syncwarp();
+        // ---- B3: assembly
+        if (keep) {
+          any = true;
+          if (t == 0) ++st_prim;
+          for (int r = 0; r < R; ++r) {
+            const double* gbase = qs + (size_t)(3 * r) * GSTR + G1 + G2;
+#pragma unroll
+            for (int j = 0; j < NVL; ++j) {
+              if (t + G * j < VL) {
+                const double* gx = gbase + obx[j];
+                const double* gy = gbase + GSTR + oby[j];
+                const double* gz = gbase + 2 * GSTR + obz[j];
+                double X_[NKL1], Y_[NKL1], Z_[NKL1];
+#pragma unroll
+                for (int k = 0; k < NKL1; ++k) { X_[k] = gx[k]; Y_[k] = gy[k]; Z_[k] = gz[k]; }
+                static_for<0, NKET>([&](auto I) {
+                  constexpr int k = decltype(I)::value;
+                  constexpr int ic = k / ND, id = k % ND;
+                  constexpr int ix = Cart<LC>::x(ic) * (LD + 1) + Cart<LD>::x(id);
+                  constexpr int iy = Cart<LC>::y(ic) * (LD + 1) + Cart<LD>::y(id);
+                  constexpr int iz = Cart<LC>::z(ic) * (LD + 1) + Cart<LD>::z(id);
+                  acc[j][k] = fma(X_[ix] * Y_[iy], Z_[iz], acc[j][k]);
+                });
+              }
+            }
+          }
+        }
+        __syncwarp();  // g tables are overwritten by the next primitive's B2; rw by its B1
+      }
+    }
+    __syncwarp();
+    // ---- block to shared memory (aliases the g tables)
+    if (valid) {
+      if (any && t == 0) qi.nonzero = 1;
+#pragma unroll
+      for (int j = 0; j < NVL; ++j) {
+        int vt = t + G * j;
+        if (vt < VL) {
+#pragma unroll
+          for (int k = 0; k < NKET; ++k) qs[(size_t)vt * NKET + k] = acc[j][k];
+        }
+      }
+    }
+    __syncwarp();
+    const bool work = valid && qi.nonzero;
+    if (valid && !qi.nonzero) {
+      if (A.mode == MODE_SCHWARZ && t == 0) A.qout[qi.bra_id] = 0.0;
+      if (A.mode == MODE_BLOCK)
+        for (int e = t; e < PT[0].nout * PT[1].nout * PT[2].nout * PT[3].nout; e += G) A.blockout[e] = 0.0;
+    }
+    double* src = qs;
+    double* dst = qs + Cfg::NCART4;
+    int n0 = NA, n1 = NB, n2 = NC, n3 = ND;
+    if (LD >= 2) {
+      if (work) proj_pass(src, dst, n0 * n1 * n2, n3, 1, PT[3], t, G);
+      n3 = PT[3].nout;
+      double* tmp = src; src = dst; dst = tmp;
+      __syncwarp();
+    }
+    if (LC >= 2) {
+      if (work) proj_pass(src, dst, n0 * n1, n2, n3, PT[2], t, G);
+      n2 = PT[2].nout;
+      double* tmp = src; src = dst; dst = tmp;
+      __syncwarp();
+    }
+    if (LB >= 2) {
+      if (work) proj_pass(src, dst, n0, n1, n2 * n3, PT[1], t, G);
+      n1 = PT[1].nout;
+      double* tmp = src; src = dst; dst = tmp;
+      __syncwarp();
+    }
+    if (LA >= 2) {
+      if (work) proj_pass(src, dst, 1, n0, n1 * n2 * n3, PT[0], t, G);
+      n0 = PT[0].nout;
+      double* tmp = src; src = dst; dst = tmp;
+      __syncwarp();
+    }
+    const int ntot = n0 * n1 * n2 * n3;
+    if (A.mode == MODE_SCHWARZ) {
+      double mx = 0.0;
+      if (work) for (int e = t; e < ntot; e += G) mx = fmax(mx, fabs(src[e]));
+#pragma unroll
+      for (int off = G / 2; off >= 1; off >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, off));
+      if (work && t == 0) A.qout[qi.bra_id] = sqrt(mx);
+      continue;
+    }
+    if (A.mode == MODE_BLOCK) {
+      if (work) for (int e = t; e < ntot; e += G) A.blockout[e] = src[e];
+      continue;
+    }
+    if (work) {
+      const double fac = (double)qi.fac, cut = A.cutoff;
+      unsigned nz = 0;
+      for (int e = t; e < ntot; e += G) {
+        double v = src[e];
+        bool z = fabs(v) < cut;
+        nz += !z;
+        src[e] = z ? 0.0 : v * fac;
+      }
+      st_ints += (unsigned long long)nz * (unsigned)(8.0f * qi.fac);
+    }
+    __syncwarp();
+    if (work) {
+      if (A.mode == MODE_SYM) digest_sym(A, src, n0, n1, n2, n3, qi.oa, qi.ob, qi.oc, qi.od, t, G);
+      else digest_gen(A, src, n0, n1, n2, n3, qi.oa, qi.ob, qi.oc, qi.od, t, G);
+    }
+  }
+  if (A.stat) {
+    if (st_prim) atomicAdd(A.stat, st_prim);
+    if (st_ints) atomicAdd(A.stat + 1, st_ints);
+  }
+}
+
 template <int LA, int LB, int LC, int LD>
 cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
   using Cfg = ClassCfg<LA, LB, LC, LD>;
@@ -928,6 +1250,17 @@ cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
     }
     eri_small_kernel<LA, LB, LC, LD, true><<<nblocks, MEDIUM_NT, smem, st>>>(args);
     return cudaGetLastError();
+  } else if constexpr (GroupCfg<LA, LB, LC, LD>::OK) {
+    using GC = GroupCfg<LA, LB, LC, LD>;
+    static bool attr_set = false;
+    if (!attr_set && GC::SMEM > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(eri_group_kernel<LA, LB, LC, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)GC::SMEM);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    eri_group_kernel<LA, LB, LC, LD><<<nblocks, GC::NT, GC::SMEM, st>>>(args);
+    return cudaGetLastError();
   } else {
     static bool attr_set = false;
     if (!attr_set) {
@@ -943,7 +1276,9 @@ cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
 
 template <int LA, int LB, int LC, int LD>
 constexpr int class_tasks_per_cta() {
-  return ClassCfg<LA, LB, LC, LD>::NCART4 <= SMALL_MAX ? SMALL_NT : (ClassCfg<LA, LB, LC, LD>::NCART4 <= MEDIUM_MAX ? MEDIUM_NT : ClassCfg<LA, LB, LC, LD>::QPB);
+  using C = ClassCfg<LA, LB, LC, LD>;
+  using GC = GroupCfg<LA, LB, LC, LD>;
+  return C::NCART4 <= SMALL_MAX ? SMALL_NT : (C::NCART4 <= MEDIUM_MAX ? MEDIUM_NT : (GC::OK ? GC::WPC * GC::QPW : C::QPB));
 }
 
 using LaunchFn = cudaError_t (*)(const EriArgs&, int, cudaStream_t);

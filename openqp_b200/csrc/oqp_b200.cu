@@ -44,6 +44,12 @@ const ClassEntry* class_table();  // eri_inst_*.cu, indexed by quartet class
 namespace {
 
 constexpr int NPC = 10;  // pair classes ss ps pp ds dp dd fs fp fd ff
+// Each pair class is split into contraction buckets (number of primitive pairs) so that the quartets of one
+// launch have similar primitive-loop lengths (one thread = one quartet in the small kernels: less divergence).
+constexpr int NBK = 4;
+constexpr int NL = NPC * NBK;  // pair lists
+inline int bucket_of(int pcnt) { return pcnt <= 1 ? 0 : (pcnt <= 6 ? 1 : (pcnt <= 24 ? 2 : 3)); }
+inline int pc_of(int list) { return list / NBK; }
 inline int pair_class(int la, int lb) { return la * (la + 1) / 2 + lb; }
 inline int quartet_class(int pa, int pb) { return pa * (pa + 1) / 2 + pb; }
 const int PC_LA[NPC] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3};
@@ -79,7 +85,7 @@ struct PairTable {
   std::vector<PairEntry> ent;
   std::vector<int> canon;  // canonical pair id tri(i,j), i>=j by shell index
   std::vector<double> Q;
-  int cls_off[NPC + 1] = {0};
+  int cls_off[NL + 1] = {0};  // offsets of the NL pair lists (class-major, bucket-minor)
   DevBuf d_ent, d_prim, d_Q, d_canon;
   long nprim = 0;
 };
@@ -203,7 +209,8 @@ __global__ void k_pairs(int nshell, long npairs, const int* __restrict__ am, con
         o[1] = (a1 * ay + a2 * by) * gi;
         o[2] = (a1 * az + a2 * bz) * gi;
         o[3] = gam;
-        o[4] = sqrtpito52 * k1;
+        o[4] = sqrtpito52 * k1 * gi;  // da = K * ginv (int_rys.F90:216)
+        o[5] = gi;
       }
       ++n;
     }
@@ -218,9 +225,9 @@ __global__ void k_pairs(int nshell, long npairs, const int* __restrict__ am, con
     for (int a = 1; a < n; ++a) {
       double rec[PRIM_STRIDE];
       for (int k = 0; k < PRIM_STRIDE; ++k) rec[k] = o[a * PRIM_STRIDE + k];
-      const double key = fabs(rec[4] / rec[3]);
+      const double key = fabs(rec[4]);
       int b = a - 1;
-      while (b >= 0 && fabs(o[b * PRIM_STRIDE + 4] / o[b * PRIM_STRIDE + 3]) < key) {
+      while (b >= 0 && fabs(o[b * PRIM_STRIDE + 4]) < key) {
         for (int k = 0; k < PRIM_STRIDE; ++k) o[(b + 1) * PRIM_STRIDE + k] = o[b * PRIM_STRIDE + k];
         --b;
       }
@@ -484,18 +491,18 @@ int build_pairtable(oqpb_ctx* ctx, const Cutoffs& c, PairTable& T, const std::ve
   CK(cudaStreamSynchronize(ctx->stream));
   d_cnt.release();
   // group by class
-  std::vector<std::vector<int>> bycls(NPC);
+  std::vector<std::vector<int>> bycls(NL);
   {
     long id = 0;
     for (int i = 0; i < ns; ++i)
       for (int j = 0; j <= i; ++j, ++id) {
         int la = ctx->am[i], lb = ctx->am[j];
         int pc = la >= lb ? pair_class(la, lb) : pair_class(lb, la);
-        bycls[pc].push_back((int)id);
+        bycls[pc * NBK + bucket_of(cnt[id])].push_back((int)id);
       }
   }
   if (Qmat) {
-    for (int pc = 0; pc < NPC; ++pc) {
+    for (int pc = 0; pc < NL; ++pc) {
       auto& v = bycls[pc];
       auto qof = [&](int id) {
         int i = (int)((std::sqrt(8.0 * id + 1.0) - 1.0) * 0.5);
@@ -512,7 +519,7 @@ int build_pairtable(oqpb_ctx* ctx, const Cutoffs& c, PairTable& T, const std::ve
   }
   T.ent.clear(); T.canon.clear(); T.Q.clear();
   long poff = 0;
-  for (int pc = 0; pc < NPC; ++pc) {
+  for (int pc = 0; pc < NL; ++pc) {
     T.cls_off[pc] = (int)T.ent.size();
     for (int id : bycls[pc]) {
       int i = (int)((std::sqrt(8.0 * id + 1.0) - 1.0) * 0.5);
@@ -530,7 +537,7 @@ int build_pairtable(oqpb_ctx* ctx, const Cutoffs& c, PairTable& T, const std::ve
       T.Q.push_back(Qmat ? (*Qmat)[(size_t)i * ns + j] : 0.0);
     }
   }
-  T.cls_off[NPC] = (int)T.ent.size();
+  T.cls_off[NL] = (int)T.ent.size();
   T.nprim = poff;
   if (poff > 2000000000L) { ctx->err = "pair table too large"; return OQPB_ERR_UNSUPPORTED; }
   int rc;
@@ -548,10 +555,11 @@ int build_pairtable(oqpb_ctx* ctx, const Cutoffs& c, PairTable& T, const std::ve
   return OQPB_OK;
 }
 
-void fill_common_args(oqpb_ctx* ctx, const PairTable& T, int pca, int pcb, EriArgs& A) {
+void fill_common_args(oqpb_ctx* ctx, const PairTable& T, int la_, int lb_, EriArgs& A) {
   memset(&A, 0, sizeof A);
-  A.bra = T.d_ent.as<PairEntry>() + T.cls_off[pca];
-  A.ket = T.d_ent.as<PairEntry>() + T.cls_off[pcb];
+  A.bra = T.d_ent.as<PairEntry>() + T.cls_off[la_];
+  A.ket = T.d_ent.as<PairEntry>() + T.cls_off[lb_];
+  const int pca = pc_of(la_), pcb = pc_of(lb_);
   A.prim = T.d_prim.as<double>();
   A.xyz = ctx->d_xyz.as<double>();
   A.aooff = ctx->d_aooff.as<int>();
@@ -590,19 +598,18 @@ int schwarz(oqpb_ctx* ctx) {
   DevBuf d_q, d_tasks, d_cnt;
   CK(d_q.ensure(nent * sizeof(double)));
   CK(cudaMemsetAsync(d_q.p, 0, nent * sizeof(double), ctx->stream));
-  CK(d_cnt.ensure(2 * NPC * sizeof(unsigned)));
-  std::vector<unsigned> hc(2 * NPC, 0);
+  CK(d_cnt.ensure(2 * NL * sizeof(unsigned)));
+  std::vector<unsigned> hc(2 * NL, 0);
   const ClassEntry* tab = class_table();
-  for (int pc = 0; pc < NPC; ++pc) {
+  for (int pc = 0; pc < NL; ++pc) {
     int n = T.cls_off[pc + 1] - T.cls_off[pc];
     hc[2 * pc] = n;
     hc[2 * pc + 1] = 0;
   }
   CK(cudaMemcpyAsync(d_cnt.p, hc.data(), hc.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
-  for (int pc = 0; pc < NPC; ++pc) {
+  for (int pc = 0; pc < NL; ++pc) {
     int n = T.cls_off[pc + 1] - T.cls_off[pc];
     if (n == 0) continue;
-    if (PC_LA[pc] > ctx->lmax) continue;
     std::vector<int2> tasks(n);
     for (int k = 0; k < n; ++k) tasks[k] = make_int2(k, k);
     CK(d_tasks.ensure(n * sizeof(int2)));
@@ -614,10 +621,10 @@ int schwarz(oqpb_ctx* ctx) {
     A.counter = d_cnt.as<unsigned>() + 2 * pc + 1;
     A.prim_cutoff = c.pair * c.pair;
     A.cutoff = 0.0;
-    A.proj = proj_for(ctx, pc, pc);
+    A.proj = proj_for(ctx, pc_of(pc), pc_of(pc));
     A.mode = MODE_SCHWARZ;
     A.qout = d_q.as<double>() + T.cls_off[pc];
-    const ClassEntry& ce = tab[quartet_class(pc, pc)];
+    const ClassEntry& ce = tab[quartet_class(pc_of(pc), pc_of(pc))];
     int nb = std::min((n + ce.qpb - 1) / ce.qpb, 148 * 16);
     CK(ce.launch(A, nb, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));  // tasks vector lifetime
@@ -675,7 +682,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   std::vector<std::pair<int, int>> cps;
   long long total_local = 0;
   const int nr = ctx->nranks, rk = ctx->rank;
-  for (int pca = 0; pca < NPC; ++pca) {
+  for (int pca = 0; pca < NL; ++pca) {  // pca / pcb are pair LISTS here (class x contraction bucket)
     int na = T.cls_off[pca + 1] - T.cls_off[pca];
     if (na == 0) continue;
     for (int pcb = 0; pcb <= pca; ++pcb) {
@@ -766,14 +773,15 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     A.counter = d_cnt + 2 * c + 1;
     A.prim_cutoff = ctx->cut.pair * ctx->cut.pair;
     A.cutoff = cutoff;
-    A.proj = proj_for(ctx, ch.pca, ch.pcb);
+    A.proj = proj_for(ctx, pc_of(ch.pca), pc_of(ch.pcb));
     A.stat = ctx->d_stats.as<unsigned long long>() + 2 * c;
     A.mode = S.mode;
     A.nmat = S.nmat;
     for (int m = 0; m < S.nmat; ++m) { A.DJ[m] = S.DJ[m]; A.DK[m] = S.DK[m]; A.F[m] = S.F[m]; }
     A.cj = S.cj; A.ck = S.ck;
     A.Pgen = S.Pgen; A.Fgen = S.Fgen; A.gen_nmat_total = S.gen_nm; A.gen_ncoul = S.gen_ncoul; A.gen_nvec = S.gen_nvec;
-    const ClassEntry& ce = tab[quartet_class(ch.pca, ch.pcb)];
+    const int qcls = quartet_class(pc_of(ch.pca), pc_of(ch.pcb));
+    const ClassEntry& ce = tab[qcls];
     size_t nb = std::min<size_t>((ch.cand + ce.qpb - 1) / ce.qpb, (size_t)148 * 32);
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (ctx->profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, ctx->stream); }
@@ -783,7 +791,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
       cudaEventSynchronize(pe1);
       float pms = 0;
       cudaEventElapsedTime(&pms, pe0, pe1);
-      ctx->prof[quartet_class(ch.pca, ch.pcb)][0] += pms;
+      ctx->prof[qcls][0] += pms;
       cudaEventDestroy(pe0); cudaEventDestroy(pe1);
     }
     ctx->st_launches += 2;
@@ -818,9 +826,10 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     // algorithmic FLOPs: primitive quartets past the int_rys.F90:232 test x F_prim(class)
     // + surviving (de-duplicated) AO integrals x digestion cost per integral
     const Chunk& ch = chunks[c];
-    double fl_c = (double)h_stats[2 * c] * fprim_model(PC_LA[ch.pca], PC_LB[ch.pca], PC_LA[ch.pcb], PC_LB[ch.pcb]);
+    const int pa_ = pc_of(ch.pca), pb_ = pc_of(ch.pcb);
+    double fl_c = (double)h_stats[2 * c] * fprim_model(PC_LA[pa_], PC_LB[pa_], PC_LA[pb_], PC_LB[pb_]);
     if (ctx->profile) {
-      double* pr = ctx->prof[quartet_class(ch.pca, ch.pcb)];
+      double* pr = ctx->prof[quartet_class(pa_, pb_)];
       pr[1] += n; pr[2] += (double)h_stats[2 * c]; pr[3] += fl_c + (double)h_stats[2 * c + 1] / 8.0 * S.digest_flops_per_int;
     }
     flops += fl_c;
@@ -1207,11 +1216,12 @@ int oqpb_eri_block(oqpb_ctx* ctx, int i, int j, int k, int l, double* out, int* 
     pc = la >= lb ? pair_class(la, lb) : pair_class(lb, la);
     int hi = std::max(a, b), lo = std::min(a, b);
     int canon = hi * (hi + 1) / 2 + lo;
-    for (int e = T.cls_off[pc]; e < T.cls_off[pc + 1]; ++e)
-      if (T.canon[e] == canon) { idx = e - T.cls_off[pc]; return; }
+    for (int lst = pc * NBK; lst < (pc + 1) * NBK; ++lst)
+      for (int e = T.cls_off[lst]; e < T.cls_off[lst + 1]; ++e)
+        if (T.canon[e] == canon) { idx = e - T.cls_off[lst]; pc = lst; return; }
     idx = -1;
   };
-  int pca, pcb, ea, eb;
+  int pca, pcb, ea, eb;  // pair lists
   find(i, j, pca, ea);
   find(k, l, pcb, eb);
   bool swapped = pca < pcb;
@@ -1230,10 +1240,10 @@ int oqpb_eri_block(oqpb_ctx* ctx, int i, int j, int k, int l, double* out, int* 
   A.ntasks = d_cnt.as<unsigned>();
   A.counter = d_cnt.as<unsigned>() + 1;
   A.prim_cutoff = ctx->cut.pair * ctx->cut.pair;
-  A.proj = proj_for(ctx, pca, pcb);
+  A.proj = proj_for(ctx, pc_of(pca), pc_of(pcb));
   A.mode = MODE_BLOCK;
   A.blockout = d_out.as<double>();
-  const ClassEntry& ce = class_table()[quartet_class(pca, pcb)];
+  const ClassEntry& ce = class_table()[quartet_class(pc_of(pca), pc_of(pcb))];
   CK(ce.launch(A, 1, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   // kernel block order: (A,B,C,D) = (bra.sa, bra.sb, ket.sa, ket.sb); map back to the caller's (i,j,k,l)
