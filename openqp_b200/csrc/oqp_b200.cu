@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -744,6 +745,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   ctx->rec.clear();
   ctx->st_launches = 0;
   std::vector<int2> rec_tmp;
+  std::vector<float> chunk_ms;
   const size_t smem_rows = (size_t)2 * ns * sizeof(double);
   const int use_smem = smem_rows <= 96 * 1024;
   static bool enum_attr = false;
@@ -792,6 +794,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
       float pms = 0;
       cudaEventElapsedTime(&pms, pe0, pe1);
       ctx->prof[qcls][0] += pms;
+      chunk_ms.push_back(pms);
       cudaEventDestroy(pe0); cudaEventDestroy(pe1);
     }
     ctx->st_launches += 2;
@@ -834,6 +837,15 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     }
     flops += fl_c;
     flops += (double)h_stats[2 * c + 1] / 8.0 * S.digest_flops_per_int;
+  }
+  if (ctx->profile && getenv("OQPB_PROF_FILE") && chunk_ms.size() == nch) {
+    // per-launch dump: pair list (class*4 + contraction bucket) of bra and ket, ms, quartets, primitive quartets
+    if (FILE* fp = fopen(getenv("OQPB_PROF_FILE"), "a")) {
+      for (size_t c = 0; c < nch; ++c)
+        fprintf(fp, "%d %d %.4f %u %llu\n", chunks[c].pca, chunks[c].pcb, chunk_ms[c], ctx->h_counts[2 * c],
+                (unsigned long long)h_stats[2 * c]);
+      fclose(fp);
+    }
   }
   ctx->st_flops = flops;
   ctx->st_survivors = surv;
