@@ -23,22 +23,27 @@
 
 namespace oqpb {
 
-struct PairEntry {
+struct alignas(16) PairEntry {
   int sa, sb;      // shells, am(sa) >= am(sb); equal am: sa is the canonical row shell (sa >= sb)
   int poff, pcnt;  // primitive-pair records, sorted by |K|/zeta descending
   double zmin;     // smallest zeta of the pair (lower bound of zeta+eta in the primitive-quartet test)
+  double ax, ay, az;     // centre of shell sa
+  double abx, aby, abz;  // A - B
+  int oa, ob;            // first AO of sa, sb
 };
 
 // primitive pair record: Px Py Pz zeta da zinv, da = K/zeta with K = sqrt(2) pi^{5/4} c_a c_b exp(-ab R^2/zeta)
 // (int2_pairs.F90:259, int_rys.F90:216); records of a pair are sorted by |da| descending
 constexpr int PRIM_STRIDE = 6;
 
-constexpr int MAX_PROJ_TERMS = 6;
-struct ProjTable {  // output row -> sparse list over my internal Cartesian order (normalisation folded in)
-  int nout;
-  int nterm[10];
-  int idx[10][MAX_PROJ_TERMS];
-  double coef[10][MAX_PROJ_TERMS];
+#include "proj_tables.inc"
+
+// pure / Cartesian variant of a kernel: bit 0 = d shells are pure (5d), bit 1 = f shells are pure (7f)
+template <int L, int PV>
+struct Shell {
+  static constexpr bool PURE = (L >= 2) && (((PV >> (L - 2)) & 1) != 0);
+  static constexpr int NC = (L + 1) * (L + 2) / 2;
+  static constexpr int NOUT = PROJC[L][PURE ? 1 : 0].nout;
 };
 
 enum Mode { MODE_SYM = 0, MODE_GEN = 1, MODE_SCHWARZ = 2, MODE_BLOCK = 3 };
@@ -59,7 +64,6 @@ struct EriArgs {
   double herm_r[7], herm_w[7];
   double prim_cutoff;  // pair_cutoff^2 (int_rys.F90:74,232)
   double cutoff;       // element cutoff (int2.F90:1806-1812)
-  const ProjTable* proj;  // 4 tables (device memory): for la, lb, lc, ld
   int mode;
   int nbf;
   // MODE_SYM: packed Fock accumulation, out_m += 4*cj*Jtype[DJ_m] - ck*Ktype[DK_m]   (reference's 6 updates)
@@ -189,109 +193,282 @@ __device__ __forceinline__ double rys_eval(const EriArgs& a, double X, int f) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// index-wise projection pass: in[(outer, j<nin, inner)] -> out[(outer, o<nout, inner)]
-__device__ __forceinline__ void proj_pass(const double* __restrict__ in, double* __restrict__ out, int outer, int nin,
-                                          int inner, const ProjTable& T, int t, int ts) {
-  const int nout = T.nout;
-  const int tot = outer * nout * inner;
-  for (int e = t; e < tot; e += ts) {
-    int i = e % inner;
-    int r = e / inner;
-    int o = r % nout;
-    int ou = r / nout;
-    const double* src = in + (size_t)ou * nin * inner + i;
-    double s = 0.0;
-    const int nt = T.nterm[o];
-    for (int k = 0; k < nt; ++k) s = fma(T.coef[o][k], src[T.idx[o][k] * inner], s);
-    out[e] = s;
+// Normalisation + Cartesian -> pure projection of ONE index of a 4-index block, tables known at compile time
+// (int2.F90:1187-1207; int_rys.F90:715-785; proj_tables.inc).  Tensor layout (OUTER, NIN, INNER) -> (OUTER, NOUT, INNER).
+// (1) block in registers (thread-per-quartet kernels): every index is a constant expression
+template <int L, bool PURE, int OUTER, int INNER, int NI, int NO>
+__device__ __forceinline__ void proj_reg(const double (&in)[NI], double (&out)[NO]) {
+  constexpr int NIN = (L + 1) * (L + 2) / 2, NOUT = PROJC[L][PURE ? 1 : 0].nout;
+  static_assert(NI == OUTER * NIN * INNER && NO == OUTER * NOUT * INNER, "proj_reg: shape");
+  if constexpr (L < 2) {
+#pragma unroll
+    for (int e = 0; e < NO; ++e) out[e] = in[e];
+  } else {
+    static_for<0, NO>([&](auto E) {
+      constexpr int e = decltype(E)::value;
+      constexpr int i = e % INNER, o = (e / INNER) % NOUT, ou = e / (INNER * NOUT);
+      constexpr int nt = PROJC[L][PURE ? 1 : 0].nterm[o];
+      double sum = 0.0;
+      static_for<0, nt>([&](auto K) {
+        constexpr int k = decltype(K)::value;
+        constexpr int j = PROJC[L][PURE ? 1 : 0].idx[o][k];
+        constexpr double c = PROJC[L][PURE ? 1 : 0].coef[o][k];
+        sum = fma(c, in[(ou * NIN + j) * INNER + i], sum);
+      });
+      out[e] = sum;
+    });
+  }
+}
+// (2) block in shared memory (team kernels): a lane transforms whole NIN-vectors, coefficients are immediates
+template <int L, bool PURE, int OUTER, int INNER>
+__device__ __forceinline__ void proj_smem(const double* __restrict__ in, double* __restrict__ out, int t, int ts) {
+  constexpr int NIN = (L + 1) * (L + 2) / 2, NOUT = PROJC[L][PURE ? 1 : 0].nout;
+  for (int e = t; e < OUTER * INNER; e += ts) {
+    const int i = e % INNER, ou = e / INNER;
+    const double* src = in + (size_t)ou * NIN * INNER + i;
+    double* dst = out + (size_t)ou * NOUT * INNER + i;
+    double x[NIN];
+#pragma unroll
+    for (int j = 0; j < NIN; ++j) x[j] = src[j * INNER];
+    static_for<0, NOUT>([&](auto O) {
+      constexpr int o = decltype(O)::value;
+      constexpr int nt = PROJC[L][PURE ? 1 : 0].nterm[o];
+      double sum = 0.0;
+      static_for<0, nt>([&](auto K) {
+        constexpr int k = decltype(K)::value;
+        constexpr int j = PROJC[L][PURE ? 1 : 0].idx[o][k];
+        constexpr double c = PROJC[L][PURE ? 1 : 0].coef[o][k];
+        sum = fma(c, x[j], sum);
+      });
+      dst[o * INNER] = sum;
+    });
   }
 }
 
 __device__ __forceinline__ size_t tri_idx(int p, int q) {
   return p >= q ? (size_t)p * (p + 1) / 2 + q : (size_t)q * (q + 1) / 2 + p;
 }
+__device__ __forceinline__ unsigned tri_u(unsigned p, unsigned q) {  // nbf <= 46000: p(p+1) < 2^32
+  return p >= q ? p * (p + 1) / 2 + q : q * (q + 1) / 2 + p;
+}
 
 // ---------------------------------------------------------------------------------------------------
-// Digestion of one finished block blk[a][b][c][d] (d fastest), dims n0..n3, AO offsets o0..o3.
+// Digestion of one finished block blk[a][b][c][d] (d fastest), compile-time dims, AO offsets o0..o3.
 // MODE_SYM: the reference's six packed updates (int2.F90:1414-1484 / 1488-1578) on the full block
-// with the shell-level coincidence factor `fac` (equivalent to the unique-AO walk + AO-level halving of
-// storeints, int2.F90:1769-1851).
-__device__ __forceinline__ void digest_sym(const EriArgs& A, const double* blk, int n0, int n1, int n2, int n3, int o0,
-                                           int o1, int o2, int o3, int t, int ts) {
-  const int nbf = A.nbf;
-  const int n23 = n2 * n3, n123 = n1 * n23;
+// with the shell-level coincidence factor already applied (equivalent to the unique-AO walk + AO-level halving
+// of storeints, int2.F90:1769-1851).  One FP64 red per Fock element per quartet.
+// (1) block in registers, one thread: everything unrolled, the density sub-block of a pass is loaded first
+template <int N0, int N1, int N2, int N3>
+__device__ __forceinline__ void digest_sym_reg(const EriArgs& A, const double (&v)[N0 * N1 * N2 * N3], int o0, int o1,
+                                               int o2, int o3) {
+  const unsigned nbf = (unsigned)A.nbf;
+  const double c4 = 4.0 * A.cj, c1 = A.ck;
+#define VV(a, b, c, d) v[(((a)*N1 + (b)) * N2 + (c)) * N3 + (d)]
+  for (int m = 0; m < A.nmat; ++m) {
+    const double* __restrict__ DJ = A.DJ[m];
+    const double* __restrict__ DK = A.DK[m];
+    double* __restrict__ F = A.F[m];
+    {  // J_ab += 4 cj sum_cd v D_cd
+      double dd[N2 * N3];
+#pragma unroll
+      for (int c = 0; c < N2; ++c)
+#pragma unroll
+        for (int d = 0; d < N3; ++d) dd[c * N3 + d] = __ldg(DJ + ((unsigned)(o2 + c) * nbf + (unsigned)(o3 + d)));
+#pragma unroll
+      for (int a = 0; a < N0; ++a)
+#pragma unroll
+        for (int b = 0; b < N1; ++b) {
+          double sum = 0.0;
+#pragma unroll
+          for (int c = 0; c < N2; ++c)
+#pragma unroll
+            for (int d = 0; d < N3; ++d) sum = fma(VV(a, b, c, d), dd[c * N3 + d], sum);
+          if (sum != 0.0) atomicAdd(F + tri_u(o0 + a, o1 + b), c4 * sum);
+        }
+    }
+    {  // J_cd += 4 cj sum_ab v D_ab
+      double dd[N0 * N1];
+#pragma unroll
+      for (int a = 0; a < N0; ++a)
+#pragma unroll
+        for (int b = 0; b < N1; ++b) dd[a * N1 + b] = __ldg(DJ + ((unsigned)(o0 + a) * nbf + (unsigned)(o1 + b)));
+#pragma unroll
+      for (int c = 0; c < N2; ++c)
+#pragma unroll
+        for (int d = 0; d < N3; ++d) {
+          double sum = 0.0;
+#pragma unroll
+          for (int a = 0; a < N0; ++a)
+#pragma unroll
+            for (int b = 0; b < N1; ++b) sum = fma(VV(a, b, c, d), dd[a * N1 + b], sum);
+          if (sum != 0.0) atomicAdd(F + tri_u(o2 + c, o3 + d), c4 * sum);
+        }
+    }
+    {  // K_ac -= ck sum_bd v D_bd
+      double dd[N1 * N3];
+#pragma unroll
+      for (int b = 0; b < N1; ++b)
+#pragma unroll
+        for (int d = 0; d < N3; ++d) dd[b * N3 + d] = __ldg(DK + ((unsigned)(o1 + b) * nbf + (unsigned)(o3 + d)));
+#pragma unroll
+      for (int a = 0; a < N0; ++a)
+#pragma unroll
+        for (int c = 0; c < N2; ++c) {
+          double sum = 0.0;
+#pragma unroll
+          for (int b = 0; b < N1; ++b)
+#pragma unroll
+            for (int d = 0; d < N3; ++d) sum = fma(VV(a, b, c, d), dd[b * N3 + d], sum);
+          if (sum != 0.0) atomicAdd(F + tri_u(o0 + a, o2 + c), -c1 * sum);
+        }
+    }
+    {  // K_ad -= ck sum_bc v D_bc
+      double dd[N1 * N2];
+#pragma unroll
+      for (int b = 0; b < N1; ++b)
+#pragma unroll
+        for (int c = 0; c < N2; ++c) dd[b * N2 + c] = __ldg(DK + ((unsigned)(o1 + b) * nbf + (unsigned)(o2 + c)));
+#pragma unroll
+      for (int a = 0; a < N0; ++a)
+#pragma unroll
+        for (int d = 0; d < N3; ++d) {
+          double sum = 0.0;
+#pragma unroll
+          for (int b = 0; b < N1; ++b)
+#pragma unroll
+            for (int c = 0; c < N2; ++c) sum = fma(VV(a, b, c, d), dd[b * N2 + c], sum);
+          if (sum != 0.0) atomicAdd(F + tri_u(o0 + a, o3 + d), -c1 * sum);
+        }
+    }
+    {  // K_bc -= ck sum_ad v D_ad
+      double dd[N0 * N3];
+#pragma unroll
+      for (int a = 0; a < N0; ++a)
+#pragma unroll
+        for (int d = 0; d < N3; ++d) dd[a * N3 + d] = __ldg(DK + ((unsigned)(o0 + a) * nbf + (unsigned)(o3 + d)));
+#pragma unroll
+      for (int b = 0; b < N1; ++b)
+#pragma unroll
+        for (int c = 0; c < N2; ++c) {
+          double sum = 0.0;
+#pragma unroll
+          for (int a = 0; a < N0; ++a)
+#pragma unroll
+            for (int d = 0; d < N3; ++d) sum = fma(VV(a, b, c, d), dd[a * N3 + d], sum);
+          if (sum != 0.0) atomicAdd(F + tri_u(o1 + b, o2 + c), -c1 * sum);
+        }
+    }
+    {  // K_bd -= ck sum_ac v D_ac
+      double dd[N0 * N2];
+#pragma unroll
+      for (int a = 0; a < N0; ++a)
+#pragma unroll
+        for (int c = 0; c < N2; ++c) dd[a * N2 + c] = __ldg(DK + ((unsigned)(o0 + a) * nbf + (unsigned)(o2 + c)));
+#pragma unroll
+      for (int b = 0; b < N1; ++b)
+#pragma unroll
+        for (int d = 0; d < N3; ++d) {
+          double sum = 0.0;
+#pragma unroll
+          for (int a = 0; a < N0; ++a)
+#pragma unroll
+            for (int c = 0; c < N2; ++c) sum = fma(VV(a, b, c, d), dd[a * N2 + c], sum);
+          if (sum != 0.0) atomicAdd(F + tri_u(o1 + b, o3 + d), -c1 * sum);
+        }
+    }
+  }
+#undef VV
+}
+
+// (2) block in shared memory, outputs strided over the ts lanes of a team
+template <int N0, int N1, int N2, int N3>
+__device__ __forceinline__ void digest_sym(const EriArgs& A, const double* blk, int o0, int o1, int o2, int o3, int t,
+                                           int ts) {
+  const unsigned nbf = (unsigned)A.nbf;
+  constexpr int N23 = N2 * N3;
   const double c4 = 4.0 * A.cj, c1 = A.ck;
   for (int m = 0; m < A.nmat; ++m) {
     const double* __restrict__ DJ = A.DJ[m];
     const double* __restrict__ DK = A.DK[m];
     double* __restrict__ F = A.F[m];
     // J_ab += 4 cj sum_cd v D_cd
-    for (int o = t; o < n0 * n1; o += ts) {
-      int a = o / n1, b = o % n1;
-      const double* v = blk + (size_t)o * n23;
-      double s = 0.0;
-      for (int c = 0; c < n2; ++c) {
-        const double* drow = DJ + (size_t)(o2 + c) * nbf + o3;
-        for (int d = 0; d < n3; ++d) s = fma(v[c * n3 + d], __ldg(drow + d), s);
+    for (int o = t; o < N0 * N1; o += ts) {
+      const int a = o / N1, b = o % N1;
+      const double* v = blk + o * N23;
+      double sum = 0.0;
+#pragma unroll
+      for (int c = 0; c < N2; ++c) {
+        const double* drow = DJ + ((unsigned)(o2 + c) * nbf + (unsigned)o3);
+#pragma unroll
+        for (int d = 0; d < N3; ++d) sum = fma(v[c * N3 + d], __ldg(drow + d), sum);
       }
-      if (s != 0.0) atomicAdd(F + tri_idx(o0 + a, o1 + b), c4 * s);
+      if (sum != 0.0) atomicAdd(F + tri_u(o0 + a, o1 + b), c4 * sum);
     }
     // J_cd += 4 cj sum_ab v D_ab
-    for (int o = t; o < n23; o += ts) {
-      int c = o / n3, d = o % n3;
-      double s = 0.0;
-      for (int a = 0; a < n0; ++a) {
-        const double* drow = DJ + (size_t)(o0 + a) * nbf + o1;
-        for (int b = 0; b < n1; ++b) s = fma(blk[(size_t)(a * n1 + b) * n23 + o], __ldg(drow + b), s);
+    for (int o = t; o < N23; o += ts) {
+      const int c = o / N3, d = o % N3;
+      double sum = 0.0;
+#pragma unroll
+      for (int a = 0; a < N0; ++a) {
+        const double* drow = DJ + ((unsigned)(o0 + a) * nbf + (unsigned)o1);
+#pragma unroll
+        for (int b = 0; b < N1; ++b) sum = fma(blk[(a * N1 + b) * N23 + o], __ldg(drow + b), sum);
       }
-      if (s != 0.0) atomicAdd(F + tri_idx(o2 + c, o3 + d), c4 * s);
+      if (sum != 0.0) atomicAdd(F + tri_u(o2 + c, o3 + d), c4 * sum);
     }
     // K_ac -= ck sum_bd v D_bd
-    for (int o = t; o < n0 * n2; o += ts) {
-      int a = o / n2, c = o % n2;
-      double s = 0.0;
-      for (int b = 0; b < n1; ++b) {
-        const double* drow = DK + (size_t)(o1 + b) * nbf + o3;
-        const double* v = blk + (size_t)(a * n1 + b) * n23 + c * n3;
-        for (int d = 0; d < n3; ++d) s = fma(v[d], __ldg(drow + d), s);
+    for (int o = t; o < N0 * N2; o += ts) {
+      const int a = o / N2, c = o % N2;
+      double sum = 0.0;
+#pragma unroll
+      for (int b = 0; b < N1; ++b) {
+        const double* drow = DK + ((unsigned)(o1 + b) * nbf + (unsigned)o3);
+        const double* v = blk + (a * N1 + b) * N23 + c * N3;
+#pragma unroll
+        for (int d = 0; d < N3; ++d) sum = fma(v[d], __ldg(drow + d), sum);
       }
-      if (s != 0.0) atomicAdd(F + tri_idx(o0 + a, o2 + c), -c1 * s);
+      if (sum != 0.0) atomicAdd(F + tri_u(o0 + a, o2 + c), -c1 * sum);
     }
     // K_ad -= ck sum_bc v D_bc
-    for (int o = t; o < n0 * n3; o += ts) {
-      int a = o / n3, d = o % n3;
-      double s = 0.0;
-      for (int b = 0; b < n1; ++b) {
-        const double* drow = DK + (size_t)(o1 + b) * nbf + o2;
-        const double* v = blk + (size_t)(a * n1 + b) * n23 + d;
-        for (int c = 0; c < n2; ++c) s = fma(v[c * n3], __ldg(drow + c), s);
+    for (int o = t; o < N0 * N3; o += ts) {
+      const int a = o / N3, d = o % N3;
+      double sum = 0.0;
+#pragma unroll
+      for (int b = 0; b < N1; ++b) {
+        const double* drow = DK + ((unsigned)(o1 + b) * nbf + (unsigned)o2);
+        const double* v = blk + (a * N1 + b) * N23 + d;
+#pragma unroll
+        for (int c = 0; c < N2; ++c) sum = fma(v[c * N3], __ldg(drow + c), sum);
       }
-      if (s != 0.0) atomicAdd(F + tri_idx(o0 + a, o3 + d), -c1 * s);
+      if (sum != 0.0) atomicAdd(F + tri_u(o0 + a, o3 + d), -c1 * sum);
     }
     // K_bc -= ck sum_ad v D_ad
-    for (int o = t; o < n1 * n2; o += ts) {
-      int b = o / n2, c = o % n2;
-      double s = 0.0;
-      for (int a = 0; a < n0; ++a) {
-        const double* drow = DK + (size_t)(o0 + a) * nbf + o3;
-        const double* v = blk + (size_t)(a * n1 + b) * n23 + c * n3;
-        for (int d = 0; d < n3; ++d) s = fma(v[d], __ldg(drow + d), s);
+    for (int o = t; o < N1 * N2; o += ts) {
+      const int b = o / N2, c = o % N2;
+      double sum = 0.0;
+#pragma unroll
+      for (int a = 0; a < N0; ++a) {
+        const double* drow = DK + ((unsigned)(o0 + a) * nbf + (unsigned)o3);
+        const double* v = blk + (a * N1 + b) * N23 + c * N3;
+#pragma unroll
+        for (int d = 0; d < N3; ++d) sum = fma(v[d], __ldg(drow + d), sum);
       }
-      if (s != 0.0) atomicAdd(F + tri_idx(o1 + b, o2 + c), -c1 * s);
+      if (sum != 0.0) atomicAdd(F + tri_u(o1 + b, o2 + c), -c1 * sum);
     }
     // K_bd -= ck sum_ac v D_ac
-    for (int o = t; o < n1 * n3; o += ts) {
-      int b = o / n3, d = o % n3;
-      double s = 0.0;
-      for (int a = 0; a < n0; ++a) {
-        const double* drow = DK + (size_t)(o0 + a) * nbf + o2;
-        const double* v = blk + (size_t)(a * n1 + b) * n23 + d;
-        for (int c = 0; c < n2; ++c) s = fma(v[c * n3], __ldg(drow + c), s);
+    for (int o = t; o < N1 * N3; o += ts) {
+      const int b = o / N3, d = o % N3;
+      double sum = 0.0;
+#pragma unroll
+      for (int a = 0; a < N0; ++a) {
+        const double* drow = DK + ((unsigned)(o0 + a) * nbf + (unsigned)o2);
+        const double* v = blk + (a * N1 + b) * N23 + d;
+#pragma unroll
+        for (int c = 0; c < N2; ++c) sum = fma(v[c * N3], __ldg(drow + c), sum);
       }
-      if (s != 0.0) atomicAdd(F + tri_idx(o1 + b, o3 + d), -c1 * s);
+      if (sum != 0.0) atomicAdd(F + tri_u(o1 + b, o3 + d), -c1 * sum);
     }
   }
-  (void)n123;
 }
 
 // MODE_GEN: general (non-symmetric) densities, all 8 permutations (tdhf_lib.F90:173-186,
@@ -301,10 +478,11 @@ __device__ __forceinline__ void digest_sym(const EriArgs& A, const double* blk, 
 //   Exchange (all m): F(a,c) -= ck v P(b,d); F(c,a) -= ck v P(d,b); F(a,d) -= ck v P(b,c); F(d,a) -= ck v P(c,b);
 //                     F(b,c) -= ck v P(a,d); F(c,b) -= ck v P(d,a); F(b,d) -= ck v P(a,c); F(d,b) -= ck v P(c,a)
 // Threads are spread over (output element, matrix): m fastest -> coalesced density reads and atomics.
-__device__ __forceinline__ void digest_gen(const EriArgs& A, const double* blk, int n0, int n1, int n2, int n3, int o0,
-                                           int o1, int o2, int o3, int t, int ts) {
+template <int n0, int n1, int n2, int n3>
+__device__ __forceinline__ void digest_gen(const EriArgs& A, const double* blk, int o0, int o1, int o2, int o3, int t,
+                                           int ts) {
   const int nbf = A.nbf, NM = A.gen_nmat_total, nv = A.gen_nvec;
-  const int n23 = n2 * n3;
+  constexpr int n23 = n2 * n3;
   const double* __restrict__ P = A.Pgen;
   double* __restrict__ F = A.Fgen;
   const int ncm = A.gen_ncoul * nv;  // interleaved index m = comp*nvec + v ... Coulomb for m < ncoul*nvec
@@ -400,9 +578,11 @@ __device__ __forceinline__ void digest_gen(const EriArgs& A, const double* blk, 
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <int LA, int LB, int LC, int LD>
+template <int LA, int LB, int LC, int LD, int PV>
 __global__ void __launch_bounds__(ClassCfg<LA, LB, LC, LD>::NT)
 eri_kernel(const EriArgs A) {
+  constexpr int N0 = Shell<LA, PV>::NOUT, N1 = Shell<LB, PV>::NOUT, N2 = Shell<LC, PV>::NOUT, N3 = Shell<LD, PV>::NOUT;
+  constexpr int NTOT = N0 * N1 * N2 * N3;
   using Cfg = ClassCfg<LA, LB, LC, LD>;
   constexpr int R = Cfg::R, TS = Cfg::TS, QPB = Cfg::QPB, NA = Cfg::NA, NB = Cfg::NB, NC = Cfg::NC, ND = Cfg::ND;
   constexpr int NMAX = Cfg::NMAX, MMAX = Cfg::MMAX, NKL1 = Cfg::NKL1, KS = Cfg::KS, TKC = Cfg::TKC;
@@ -432,7 +612,6 @@ eri_kernel(const EriArgs A) {
   const int obx = (ax * (LB + 1) + bx) * NKL1, oby = (ay * (LB + 1) + by) * NKL1, obz = (az * (LB + 1) + bz) * NKL1;
 
   const unsigned ntasks = *A.ntasks;
-  const ProjTable* PT = A.proj;
   unsigned long long st_prim = 0, st_ints = 0;
 
   for (;;) {
@@ -656,7 +835,7 @@ eri_kernel(const EriArgs A) {
     if (!(valid && qi.nonzero)) {
       if (valid && A.mode == MODE_SCHWARZ && t == 0) A.qout[qi.bra_id] = 0.0;
       if (valid && A.mode == MODE_BLOCK) {
-        for (int e = t; e < PT[0].nout * PT[1].nout * PT[2].nout * PT[3].nout; e += TS) A.blockout[e] = 0.0;
+        for (int e = t; e < NTOT; e += TS) A.blockout[e] = 0.0;
       }
       // all teams still take part in the barriers below
     }
@@ -664,33 +843,28 @@ eri_kernel(const EriArgs A) {
     // dims (a,b,c,d) -> transform d, c, b, a ; ping-pong between region 0 and region 1
     double* src = qs;
     double* dst = qs + Cfg::NCART4;
-    int n0 = NA, n1 = NB, n2 = NC, n3 = ND;
     const bool work = valid && qi.nonzero;
     if (LD >= 2) {
-      if (work) proj_pass(src, dst, n0 * n1 * n2, n3, 1, PT[3], t, TS);
-      n3 = PT[3].nout;
+      if (work) proj_smem<LD, Shell<LD, PV>::PURE, NA * NB * NC, 1>(src, dst, t, TS);
       double* tmp = src; src = dst; dst = tmp;
       __syncthreads();
     }
     if (LC >= 2) {
-      if (work) proj_pass(src, dst, n0 * n1, n2, n3, PT[2], t, TS);
-      n2 = PT[2].nout;
+      if (work) proj_smem<LC, Shell<LC, PV>::PURE, NA * NB, N3>(src, dst, t, TS);
       double* tmp = src; src = dst; dst = tmp;
       __syncthreads();
     }
     if (LB >= 2) {
-      if (work) proj_pass(src, dst, n0, n1, n2 * n3, PT[1], t, TS);
-      n1 = PT[1].nout;
+      if (work) proj_smem<LB, Shell<LB, PV>::PURE, NA, N2 * N3>(src, dst, t, TS);
       double* tmp = src; src = dst; dst = tmp;
       __syncthreads();
     }
     if (LA >= 2) {
-      if (work) proj_pass(src, dst, 1, n0, n1 * n2 * n3, PT[0], t, TS);
-      n0 = PT[0].nout;
+      if (work) proj_smem<LA, Shell<LA, PV>::PURE, 1, N1 * N2 * N3>(src, dst, t, TS);
       double* tmp = src; src = dst; dst = tmp;
       __syncthreads();
     }
-    const int ntot = n0 * n1 * n2 * n3;
+    constexpr int ntot = NTOT;
     if (A.mode == MODE_SCHWARZ) {
       // Q = sqrt(max |(ij|ij)|), int2.F90:1727-1728
       if (work) {
@@ -724,8 +898,8 @@ eri_kernel(const EriArgs A) {
     }
     __syncthreads();
     if (work) {
-      if (A.mode == MODE_SYM) digest_sym(A, src, n0, n1, n2, n3, qi.oa, qi.ob, qi.oc, qi.od, t, TS);
-      else digest_gen(A, src, n0, n1, n2, n3, qi.oa, qi.ob, qi.oc, qi.od, t, TS);
+      if (A.mode == MODE_SYM) digest_sym<N0, N1, N2, N3>(A, src, qi.oa, qi.ob, qi.oc, qi.od, t, TS);
+      else digest_gen<N0, N1, N2, N3>(A, src, qi.oa, qi.ob, qi.oc, qi.od, t, TS);
     }
   }
   if (A.stat) {
@@ -745,7 +919,55 @@ constexpr int SMALL_MAX = 36;
 constexpr int MEDIUM_MAX = 100;
 constexpr int SMALL_NT = 128, MEDIUM_NT = 64;
 
-template <int LA, int LB, int LC, int LD, bool GS>
+// Rys evaluation state at X shared by all roots and weights of a primitive quartet
+struct RysX {
+  bool asym;
+  int iv;
+  double rx, rs, t;
+};
+__device__ __forceinline__ RysX rys_prepare(const EriArgs& a, double X) {
+  RysX s;
+  s.asym = X >= (double)a.rys_xmax;
+  s.iv = 0;
+  s.rx = s.rs = s.t = 0.0;
+  if (s.asym) {
+    s.rx = 1.0 / X;  // half-range Gauss-Hermite asymptote (rys.F90:2711-2713)
+    s.rs = sqrt(s.rx);
+  } else {
+    s.iv = (int)X;
+    s.t = 2.0 * (X - (double)s.iv) - 1.0;
+  }
+  return s;
+}
+// root r (as t^2) and its weight: two interleaved Clenshaw recurrences over 16-byte table loads
+template <int R>
+__device__ __forceinline__ void rys_pair(const EriArgs& a, const RysX& s, int r, double& t2, double& w) {
+  if (s.asym) {
+    t2 = a.herm_r[r] * s.rx;
+    w = a.herm_w[r] * s.rs;
+    return;
+  }
+  const double2* __restrict__ ct = reinterpret_cast<const double2*>(a.rys_tab + ((size_t)s.iv * (2 * R) + r) * 12);
+  const double2* __restrict__ cw = ct + 6 * R;
+  double2 p[6], q[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { p[k] = __ldg(ct + k); q[k] = __ldg(cw + k); }
+  const double x2 = 2.0 * s.t;
+  double b1 = 0.0, b2 = 0.0, e1 = 0.0, e2 = 0.0;
+#pragma unroll
+  for (int k = 11; k >= 1; --k) {
+    const double ck = (k & 1) ? p[k >> 1].y : p[k >> 1].x;
+    const double dk = (k & 1) ? q[k >> 1].y : q[k >> 1].x;
+    const double b0 = fma(x2, b1, ck - b2);
+    const double e0 = fma(x2, e1, dk - e2);
+    b2 = b1; b1 = b0;
+    e2 = e1; e1 = e0;
+  }
+  t2 = fma(s.t, b1, p[0].x - b2);
+  w = fma(s.t, e1, q[0].x - e2);
+}
+
+template <int LA, int LB, int LC, int LD, int PV, bool GS>
 __global__ void __launch_bounds__(GS ? MEDIUM_NT : SMALL_NT)
 eri_small_kernel(const EriArgs A) {
   constexpr int NTH = GS ? MEDIUM_NT : SMALL_NT;
@@ -753,17 +975,16 @@ eri_small_kernel(const EriArgs A) {
   using Cfg = ClassCfg<LA, LB, LC, LD>;
   constexpr int R = Cfg::R, NA = Cfg::NA, NB = Cfg::NB, NC = Cfg::NC, ND = Cfg::ND, NCART4 = Cfg::NCART4;
   constexpr int NMAX = Cfg::NMAX, MMAX = Cfg::MMAX, NKL1 = Cfg::NKL1, NIJ1 = Cfg::NIJ1;
+  constexpr int N0 = Shell<LA, PV>::NOUT, N1 = Shell<LB, PV>::NOUT, N2 = Shell<LC, PV>::NOUT, N3 = Shell<LD, PV>::NOUT;
+  constexpr int NTOT = N0 * N1 * N2 * N3;
   const unsigned ntasks = *A.ntasks;
-  const ProjTable* PT = A.proj;
   unsigned long long st_prim = 0, st_ints = 0;
   for (unsigned ti = blockIdx.x * blockDim.x + threadIdx.x; ti < ntasks; ti += gridDim.x * blockDim.x) {
     const int2 tk = A.tasks[ti];
     const PairEntry pb = A.bra[tk.x], pk = A.ket[tk.y];
-    const double* xa = A.xyz + 3 * pb.sa; const double* xb = A.xyz + 3 * pb.sb;
-    const double* xc = A.xyz + 3 * pk.sa; const double* xd = A.xyz + 3 * pk.sb;
-    const double Ax = xa[0], Ay = xa[1], Az = xa[2], Cx = xc[0], Cy = xc[1], Cz = xc[2];
-    const double AB[3] = {Ax - xb[0], Ay - xb[1], Az - xb[2]};
-    const double CD[3] = {Cx - xd[0], Cy - xd[1], Cz - xd[2]};
+    const double Ax = pb.ax, Ay = pb.ay, Az = pb.az, Cx = pk.ax, Cy = pk.ay, Cz = pk.az;
+    const double AB[3] = {pb.abx, pb.aby, pb.abz};
+    const double CD[3] = {pk.abx, pk.aby, pk.abz};
     double acc[NCART4];
 #pragma unroll
     for (int k = 0; k < NCART4; ++k) acc[k] = 0.0;
@@ -773,18 +994,20 @@ eri_small_kernel(const EriArgs A) {
     double da0 = 0.0;
     if (pb.pcnt > 0) { const double* p0 = A.prim + (size_t)pb.poff * PRIM_STRIDE; da0 = __ldg(p0 + 4); }
     for (int kq = 0; kq < pk.pcnt; ++kq) {
-      const double* pq = A.prim + (size_t)(pk.poff + kq) * PRIM_STRIDE;
-      const double eta = __ldg(pq + 3), db = __ldg(pq + 4), einv = __ldg(pq + 5);
+      const double2* pq = reinterpret_cast<const double2*>(A.prim + (size_t)(pk.poff + kq) * PRIM_STRIDE);
+      const double2 q01 = __ldg(pq), q23 = __ldg(pq + 1), q45 = __ldg(pq + 2);
+      const double Qx = q01.x, Qy = q01.y, Qz = q23.x, eta = q23.y, db = q45.x, einv = q45.y;
       if ((da0 * db) * (da0 * db) < thr) break;
-      const double Qx = __ldg(pq), Qy = __ldg(pq + 1), Qz = __ldg(pq + 2);
       for (int kp = 0; kp < pb.pcnt; ++kp) {
-        const double* pp = A.prim + (size_t)(pb.poff + kp) * PRIM_STRIDE;
-        const double zeta = __ldg(pp + 3), zinv = __ldg(pp + 5);
-        const double pfac = __ldg(pp + 4) * db;
+        const double2* pp = reinterpret_cast<const double2*>(A.prim + (size_t)(pb.poff + kp) * PRIM_STRIDE);
+        const double2 p23 = __ldg(pp + 1), p45 = __ldg(pp + 2);
+        const double zeta = p23.y, zinv = p45.y;
+        const double pfac = p45.x * db;
         if (pfac * pfac < thr) break;
         const double ab = zeta + eta;
         if (pfac * pfac < A.prim_cutoff * ab) continue;  // int_rys.F90:229-232
-        const double Px = __ldg(pp), Py = __ldg(pp + 1), Pz = __ldg(pp + 2);
+        const double2 p01 = __ldg(pp);
+        const double Px = p01.x, Py = p01.y, Pz = p23.x;
         any = true;
         ++st_prim;
         const double abinv = 1.0 / ab;
@@ -795,10 +1018,11 @@ eri_small_kernel(const EriArgs A) {
         const double X = rho * (PQ[0] * PQ[0] + PQ[1] * PQ[1] + PQ[2] * PQ[2]);
         const double pref = pfac * sqrt(abinv);
         const double rz = rho * zinv, re = rho * einv, hz = 0.5 * zinv, he = 0.5 * einv;
+        const RysX rx = rys_prepare(A, X);
 #pragma unroll 1
         for (int r = 0; r < R; ++r) {
-          const double t2 = rys_eval<R>(A, X, r);
-          const double w = rys_eval<R>(A, X, R + r);
+          double t2, w;
+          rys_pair<R>(A, rx, r, t2, w);
           const double b10 = hz * (1.0 - t2 * rz), b01 = he * (1.0 - t2 * re), b00 = 0.5 * t2 * abinv;
           constexpr int G3 = NIJ1 * NKL1;
           double g[GS ? 1 : 3][GS ? 1 : G3];
@@ -864,47 +1088,50 @@ eri_small_kernel(const EriArgs A) {
     if (!any) {
       if (A.mode == MODE_SCHWARZ) A.qout[tk.x] = 0.0;
       if (A.mode == MODE_BLOCK)
-        for (int e = 0; e < PT[0].nout * PT[1].nout * PT[2].nout * PT[3].nout; ++e) A.blockout[e] = 0.0;
+        for (int e = 0; e < NTOT; ++e) A.blockout[e] = 0.0;
       continue;
     }
-    // block in thread-local memory; index-wise normalisation / projection, then the shared digestion code
-    double blk0[NCART4], blk1[NCART4];
-#pragma unroll
-    for (int k = 0; k < NCART4; ++k) blk0[k] = acc[k];
-    double* src = blk0;
-    double* dst = blk1;
-    int n0 = NA, n1 = NB, n2 = NC, n3 = ND;
-    if (LD >= 2) { proj_pass(src, dst, n0 * n1 * n2, n3, 1, PT[3], 0, 1); n3 = PT[3].nout; double* tmp = src; src = dst; dst = tmp; }
-    if (LC >= 2) { proj_pass(src, dst, n0 * n1, n2, n3, PT[2], 0, 1); n2 = PT[2].nout; double* tmp = src; src = dst; dst = tmp; }
-    if (LB >= 2) { proj_pass(src, dst, n0, n1, n2 * n3, PT[1], 0, 1); n1 = PT[1].nout; double* tmp = src; src = dst; dst = tmp; }
-    if (LA >= 2) { proj_pass(src, dst, 1, n0, n1 * n2 * n3, PT[0], 0, 1); n0 = PT[0].nout; double* tmp = src; src = dst; dst = tmp; }
-    const int ntot = n0 * n1 * n2 * n3;
+    // normalisation / pure projection in registers, index by index: d, c, b, a
+    double b3[NA * NB * NC * N3], b2[NA * NB * N2 * N3], b1[NA * N1 * N2 * N3], blk[NTOT];
+    proj_reg<LD, Shell<LD, PV>::PURE, NA * NB * NC, 1>(acc, b3);
+    proj_reg<LC, Shell<LC, PV>::PURE, NA * NB, N3>(b3, b2);
+    proj_reg<LB, Shell<LB, PV>::PURE, NA, N2 * N3>(b2, b1);
+    proj_reg<LA, Shell<LA, PV>::PURE, 1, N1 * N2 * N3>(b1, blk);
     if (A.mode == MODE_SCHWARZ) {
       double mx = 0.0;
-      for (int e = 0; e < ntot; ++e) mx = fmax(mx, fabs(src[e]));
+#pragma unroll
+      for (int e = 0; e < NTOT; ++e) mx = fmax(mx, fabs(blk[e]));
       A.qout[tk.x] = sqrt(mx);
       continue;
     }
     if (A.mode == MODE_BLOCK) {
-      for (int e = 0; e < ntot; ++e) A.blockout[e] = src[e];
+#pragma unroll
+      for (int e = 0; e < NTOT; ++e) A.blockout[e] = blk[e];
       continue;
     }
+    // element cutoff (int2.F90:1806-1812) and shell-level coincidence factor (int2.F90:1849-1851)
     float facf = 1.0f;
     if (pb.sa == pb.sb) facf *= 0.5f;
     if (pk.sa == pk.sb) facf *= 0.5f;
     if (pb.sa == pk.sa && pb.sb == pk.sb) facf *= 0.5f;
     const double fac = (double)facf, cut = A.cutoff;
     unsigned nz = 0;
-    for (int e = 0; e < ntot; ++e) {
-      double v = src[e];
-      bool z = fabs(v) < cut;
+#pragma unroll
+    for (int e = 0; e < NTOT; ++e) {
+      const double v = blk[e];
+      const bool z = fabs(v) < cut;
       nz += !z;
-      src[e] = z ? 0.0 : v * fac;
+      blk[e] = z ? 0.0 : v * fac;
     }
     st_ints += (unsigned long long)nz * (unsigned)(8.0f * facf);
-    const int oa = A.aooff[pb.sa], ob = A.aooff[pb.sb], oc = A.aooff[pk.sa], od = A.aooff[pk.sb];
-    if (A.mode == MODE_SYM) digest_sym(A, src, n0, n1, n2, n3, oa, ob, oc, od, 0, 1);
-    else digest_gen(A, src, n0, n1, n2, n3, oa, ob, oc, od, 0, 1);
+    if (A.mode == MODE_SYM) {
+      digest_sym_reg<N0, N1, N2, N3>(A, blk, pb.oa, pb.ob, pk.oa, pk.ob);
+    } else {
+      double loc[NTOT];
+#pragma unroll
+      for (int e = 0; e < NTOT; ++e) loc[e] = blk[e];
+      digest_gen<N0, N1, N2, N3>(A, loc, pb.oa, pb.ob, pk.oa, pk.ob, 0, 1);
+    }
   }
   if (A.stat) {
     if (st_prim) atomicAdd(A.stat, st_prim);
@@ -936,9 +1163,11 @@ struct GroupCfg {
   static constexpr size_t SMEM = (size_t)WPC * QPW * QBYTES;
 };
 
-template <int LA, int LB, int LC, int LD>
+template <int LA, int LB, int LC, int LD, int PV>
 __global__ void __launch_bounds__(GroupCfg<LA, LB, LC, LD>::NT)
 eri_group_kernel(const EriArgs A) {
+  constexpr int N0 = Shell<LA, PV>::NOUT, N1 = Shell<LB, PV>::NOUT, N2 = Shell<LC, PV>::NOUT, N3 = Shell<LD, PV>::NOUT;
+  constexpr int NTOT = N0 * N1 * N2 * N3;
   using Cfg = ClassCfg<LA, LB, LC, LD>;
   using GC = GroupCfg<LA, LB, LC, LD>;
   constexpr int R = Cfg::R, NA = Cfg::NA, NB = Cfg::NB, NC = Cfg::NC, ND = Cfg::ND, NKET = Cfg::NKET;
@@ -970,7 +1199,6 @@ eri_group_kernel(const EriArgs A) {
     obx[j] = (ax * (LB + 1) + bx) * NKL1; oby[j] = (ay * (LB + 1) + by) * NKL1; obz[j] = (az * (LB + 1) + bz) * NKL1;
   }
   const unsigned ntasks = *A.ntasks;
-  const ProjTable* PT = A.proj;
   unsigned long long st_prim = 0, st_ints = 0;
 
   for (;;) {
@@ -1168,36 +1396,31 @@ eri_group_kernel(const EriArgs A) {
     if (valid && !qi.nonzero) {
       if (A.mode == MODE_SCHWARZ && t == 0) A.qout[qi.bra_id] = 0.0;
       if (A.mode == MODE_BLOCK)
-        for (int e = t; e < PT[0].nout * PT[1].nout * PT[2].nout * PT[3].nout; e += G) A.blockout[e] = 0.0;
+        for (int e = t; e < NTOT; e += G) A.blockout[e] = 0.0;
     }
     double* src = qs;
     double* dst = qs + Cfg::NCART4;
-    int n0 = NA, n1 = NB, n2 = NC, n3 = ND;
     if (LD >= 2) {
-      if (work) proj_pass(src, dst, n0 * n1 * n2, n3, 1, PT[3], t, G);
-      n3 = PT[3].nout;
+      if (work) proj_smem<LD, Shell<LD, PV>::PURE, NA * NB * NC, 1>(src, dst, t, G);
       double* tmp = src; src = dst; dst = tmp;
       __syncwarp();
     }
     if (LC >= 2) {
-      if (work) proj_pass(src, dst, n0 * n1, n2, n3, PT[2], t, G);
-      n2 = PT[2].nout;
+      if (work) proj_smem<LC, Shell<LC, PV>::PURE, NA * NB, N3>(src, dst, t, G);
       double* tmp = src; src = dst; dst = tmp;
       __syncwarp();
     }
     if (LB >= 2) {
-      if (work) proj_pass(src, dst, n0, n1, n2 * n3, PT[1], t, G);
-      n1 = PT[1].nout;
+      if (work) proj_smem<LB, Shell<LB, PV>::PURE, NA, N2 * N3>(src, dst, t, G);
       double* tmp = src; src = dst; dst = tmp;
       __syncwarp();
     }
     if (LA >= 2) {
-      if (work) proj_pass(src, dst, 1, n0, n1 * n2 * n3, PT[0], t, G);
-      n0 = PT[0].nout;
+      if (work) proj_smem<LA, Shell<LA, PV>::PURE, 1, N1 * N2 * N3>(src, dst, t, G);
       double* tmp = src; src = dst; dst = tmp;
       __syncwarp();
     }
-    const int ntot = n0 * n1 * n2 * n3;
+    constexpr int ntot = NTOT;
     if (A.mode == MODE_SCHWARZ) {
       double mx = 0.0;
       if (work) for (int e = t; e < ntot; e += G) mx = fmax(mx, fabs(src[e]));
@@ -1223,8 +1446,8 @@ eri_group_kernel(const EriArgs A) {
     }
     __syncwarp();
     if (work) {
-      if (A.mode == MODE_SYM) digest_sym(A, src, n0, n1, n2, n3, qi.oa, qi.ob, qi.oc, qi.od, t, G);
-      else digest_gen(A, src, n0, n1, n2, n3, qi.oa, qi.ob, qi.oc, qi.od, t, G);
+      if (A.mode == MODE_SYM) digest_sym<N0, N1, N2, N3>(A, src, qi.oa, qi.ob, qi.oc, qi.od, t, G);
+      else digest_gen<N0, N1, N2, N3>(A, src, qi.oa, qi.ob, qi.oc, qi.od, t, G);
     }
   }
   if (A.stat) {
@@ -1233,43 +1456,43 @@ eri_group_kernel(const EriArgs A) {
   }
 }
 
-template <int LA, int LB, int LC, int LD>
+template <int LA, int LB, int LC, int LD, int PV>
 cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
   using Cfg = ClassCfg<LA, LB, LC, LD>;
   if constexpr (Cfg::NCART4 <= SMALL_MAX) {
-    eri_small_kernel<LA, LB, LC, LD, false><<<nblocks, SMALL_NT, 0, st>>>(args);
+    eri_small_kernel<LA, LB, LC, LD, PV, false><<<nblocks, SMALL_NT, 0, st>>>(args);
     return cudaGetLastError();
   } else if constexpr (Cfg::NCART4 <= MEDIUM_MAX) {
     constexpr size_t smem = (size_t)3 * Cfg::NIJ1 * Cfg::NKL1 * MEDIUM_NT * sizeof(double);
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(eri_small_kernel<LA, LB, LC, LD, true>,
+      cudaError_t e = cudaFuncSetAttribute(eri_small_kernel<LA, LB, LC, LD, PV, true>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
-    eri_small_kernel<LA, LB, LC, LD, true><<<nblocks, MEDIUM_NT, smem, st>>>(args);
+    eri_small_kernel<LA, LB, LC, LD, PV, true><<<nblocks, MEDIUM_NT, smem, st>>>(args);
     return cudaGetLastError();
   } else if constexpr (GroupCfg<LA, LB, LC, LD>::OK) {
     using GC = GroupCfg<LA, LB, LC, LD>;
     static bool attr_set = false;
     if (!attr_set && GC::SMEM > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(eri_group_kernel<LA, LB, LC, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)GC::SMEM);
+      cudaError_t e = cudaFuncSetAttribute(eri_group_kernel<LA, LB, LC, LD, PV>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GC::SMEM);
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
-    eri_group_kernel<LA, LB, LC, LD><<<nblocks, GC::NT, GC::SMEM, st>>>(args);
+    eri_group_kernel<LA, LB, LC, LD, PV><<<nblocks, GC::NT, GC::SMEM, st>>>(args);
     return cudaGetLastError();
   } else {
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(eri_kernel<LA, LB, LC, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaError_t e = cudaFuncSetAttribute(eri_kernel<LA, LB, LC, LD, PV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)Cfg::SMEM);
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
-    eri_kernel<LA, LB, LC, LD><<<nblocks, Cfg::NT, Cfg::SMEM, st>>>(args);
+    eri_kernel<LA, LB, LC, LD, PV><<<nblocks, Cfg::NT, Cfg::SMEM, st>>>(args);
     return cudaGetLastError();
   }
 }
@@ -1283,5 +1506,7 @@ constexpr int class_tasks_per_cta() {
 
 using LaunchFn = cudaError_t (*)(const EriArgs&, int, cudaStream_t);
 struct ClassEntry { LaunchFn launch; int qpb; int nt; size_t smem; };
+// class table: [pure variant PV = (d pure) | (f pure) << 1][quartet class]
+const ClassEntry* class_table(int pv);
 
 }  // namespace oqpb

@@ -22,13 +22,12 @@
 
 #include "../../include/oqp_b200.h"
 #include "eri_kernel.cuh"
-#include "pure_tables.inc"
 #include "rys_tables.inc"
 
 using namespace oqpb;
 
 namespace oqpb {
-const ClassEntry* class_table();  // eri_inst_*.cu, indexed by quartet class
+const ClassEntry* class_table(int pv);  // eri_inst_*.cu: [pure variant][quartet class]
 }
 
 #define CK(call)                                                                                   \
@@ -131,7 +130,7 @@ struct oqpb_ctx {
   bool have_basis = false, have_cutoff = false, have_screen = false;
   // device basis
   DevBuf d_am, d_ncontr, d_goff, d_aooff, d_naos, d_ex, d_cc, d_xyz;
-  DevBuf d_rys, d_proj;  // Rys tables, 4 x ProjTable (per l, for the ctx's pure flags)
+  DevBuf d_rys;  // Rys tables
   double cutoff = 5e-11;
   Cutoffs cut{};
   PairTable run;
@@ -432,43 +431,6 @@ int upload(oqpb_ctx* ctx, DevBuf& b, const std::vector<T>& v) {
   return OQPB_OK;
 }
 
-// projection table for shell type l: rows = reference output order (pure CCA order or reference Cartesian
-// order), columns = my internal Cartesian order; unit normalisation (shells_pnrm2, constants.F90:121-164) folded in
-void build_proj(int l, int pure, ProjTable& T) {
-  static const int RX[4][10] = {{0}, {1, 0, 0}, {2, 0, 0, 1, 1, 0}, {3, 0, 0, 2, 2, 1, 0, 1, 0, 1}};
-  static const int RY[4][10] = {{0}, {0, 1, 0}, {0, 2, 0, 1, 0, 1}, {0, 3, 0, 1, 0, 2, 2, 0, 1, 1}};
-  memset(&T, 0, sizeof T);
-  int nc = ncart(l);
-  auto my_index = [&](int x, int y) {
-    int k = 0;
-    for (int xx = l; xx >= 0; --xx)
-      for (int yy = l - xx; yy >= 0; --yy) {
-        if (xx == x && yy == y) return k;
-        ++k;
-      }
-    return -1;
-  };
-  auto df = [](int n) { double r = 1; for (int k = n; k > 1; k -= 2) r *= k; return r; };
-  T.nout = (pure && l >= 2) ? 2 * l + 1 : nc;
-  for (int rc = 0; rc < nc; ++rc) {  // reference Cartesian component rc
-    int x = RX[l][rc], y = RY[l][rc], z = l - x - y;
-    double pn = std::sqrt(df(2 * l - 1) / (df(2 * x - 1) * df(2 * y - 1) * df(2 * z - 1)));
-    int mi = my_index(x, y);
-    if (pure && l >= 2) {
-      for (int t = 0; t < PURE_NTERM_H[l - 2][rc]; ++t) {
-        int o = PURE_OUT_H[l - 2][rc][t];
-        int k = T.nterm[o]++;
-        T.idx[o][k] = mi;
-        T.coef[o][k] = PURE_COEF_H[l - 2][rc][t] * pn;
-      }
-    } else {
-      T.nterm[rc] = 1;
-      T.idx[rc][0] = mi;
-      T.coef[rc][0] = pn;
-    }
-  }
-}
-
 int free_pairtable(PairTable& t) {
   t.d_ent.release(); t.d_prim.release(); t.d_Q.release(); t.d_canon.release();
   t.ent.clear(); t.canon.clear(); t.Q.clear();
@@ -532,6 +494,11 @@ int build_pairtable(oqpb_ctx* ctx, const Cutoffs& c, PairTable& T, const std::ve
       e.poff = (int)poff;
       e.pcnt = cnt[id];
       e.zmin = 0.0;
+      const double* xa = &ctx->cen[3 * e.sa];
+      const double* xb = &ctx->cen[3 * e.sb];
+      e.ax = xa[0]; e.ay = xa[1]; e.az = xa[2];
+      e.abx = xa[0] - xb[0]; e.aby = xa[1] - xb[1]; e.abz = xa[2] - xb[2];
+      e.oa = ctx->aooff[e.sa]; e.ob = ctx->aooff[e.sb];
       poff += cnt[id];
       T.ent.push_back(e);
       T.canon.push_back(id);
@@ -569,13 +536,6 @@ void fill_common_args(oqpb_ctx* ctx, const PairTable& T, int la_, int lb_, EriAr
   A.rys_xmax = RYS_XMAX_H[R - 1];
   for (int k = 0; k < 7; ++k) { A.herm_r[k] = RYS_HERM_R_H[R - 1][k]; A.herm_w[k] = RYS_HERM_W_H[R - 1][k]; }
   A.nbf = ctx->nbf;
-  // projection tables for (la, lb, lc, ld): device array of 4 ProjTables per quartet class is assembled on the fly
-}
-
-// device array with the 4 projection tables of a quartet class (index = l, ctx-wide pure flag per l)
-const ProjTable* proj_for(oqpb_ctx* ctx, int pca, int pcb) {
-  // d_proj holds 55 x 4 tables
-  return ctx->d_proj.as<ProjTable>() + (size_t)quartet_class(pca, pcb) * 4;
 }
 
 int ensure_counts(oqpb_ctx* ctx, size_t n) {
@@ -601,7 +561,7 @@ int schwarz(oqpb_ctx* ctx) {
   CK(cudaMemsetAsync(d_q.p, 0, nent * sizeof(double), ctx->stream));
   CK(d_cnt.ensure(2 * NL * sizeof(unsigned)));
   std::vector<unsigned> hc(2 * NL, 0);
-  const ClassEntry* tab = class_table();
+  const ClassEntry* tab = class_table(ctx->pure_l[2] | (ctx->pure_l[3] << 1));
   for (int pc = 0; pc < NL; ++pc) {
     int n = T.cls_off[pc + 1] - T.cls_off[pc];
     hc[2 * pc] = n;
@@ -622,7 +582,6 @@ int schwarz(oqpb_ctx* ctx) {
     A.counter = d_cnt.as<unsigned>() + 2 * pc + 1;
     A.prim_cutoff = c.pair * c.pair;
     A.cutoff = 0.0;
-    A.proj = proj_for(ctx, pc_of(pc), pc_of(pc));
     A.mode = MODE_SCHWARZ;
     A.qout = d_q.as<double>() + T.cls_off[pc];
     const ClassEntry& ce = tab[quartet_class(pc_of(pc), pc_of(pc))];
@@ -741,7 +700,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   CK(ctx->d_stats.ensure((2 * nch + 2) * sizeof(unsigned long long)));
   CK(cudaMemsetAsync(ctx->d_stats.p, 0, (2 * nch + 2) * sizeof(unsigned long long), ctx->stream));
   std::vector<unsigned long long> h_stats(2 * nch + 2, 0);
-  const ClassEntry* tab = class_table();
+  const ClassEntry* tab = class_table(ctx->pure_l[2] | (ctx->pure_l[3] << 1));
   ctx->rec.clear();
   ctx->st_launches = 0;
   std::vector<int2> rec_tmp;
@@ -775,7 +734,6 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     A.counter = d_cnt + 2 * c + 1;
     A.prim_cutoff = ctx->cut.pair * ctx->cut.pair;
     A.cutoff = cutoff;
-    A.proj = proj_for(ctx, pc_of(ch.pca), pc_of(ch.pcb));
     A.stat = ctx->d_stats.as<unsigned long long>() + 2 * c;
     A.mode = S.mode;
     A.nmat = S.nmat;
@@ -896,7 +854,7 @@ void oqpb_ctx_destroy(oqpb_ctx* ctx) {
   if (g_default_ctx == ctx) g_default_ctx = nullptr;
   free_pairtable(ctx->run);
   for (DevBuf* b : {&ctx->d_am, &ctx->d_ncontr, &ctx->d_goff, &ctx->d_aooff, &ctx->d_naos, &ctx->d_ex, &ctx->d_cc,
-                    &ctx->d_xyz, &ctx->d_rys, &ctx->d_proj, &ctx->d_Qmat, &ctx->d_dsh, &ctx->d_maxden, &ctx->d_ok,
+                    &ctx->d_xyz, &ctx->d_rys, &ctx->d_Qmat, &ctx->d_dsh, &ctx->d_maxden, &ctx->d_ok,
                     &ctx->d_d4, &ctx->d_rowsbuf, &ctx->d_tasks, &ctx->d_counters, &ctx->d_Dsq, &ctx->d_F, &ctx->d_Din,
                     &ctx->d_stats, &ctx->d_gen_in, &ctx->d_gen_out})
     b->release();
@@ -943,16 +901,6 @@ int oqpb_set_basis(oqpb_ctx* ctx, int nshell, int nprim, const int* am, const in
   if ((rc = upload(ctx, ctx->d_ex, ctx->ex))) return rc;
   if ((rc = upload(ctx, ctx->d_cc, ctx->cc))) return rc;
   if ((rc = upload(ctx, ctx->d_xyz, ctx->cen))) return rc;
-  // projection tables per quartet class
-  std::vector<ProjTable> pt(55 * 4);
-  ProjTable per_l[4];
-  for (int l = 0; l < 4; ++l) build_proj(l, ctx->pure_l[l], per_l[l]);
-  for (int pa = 0; pa < NPC; ++pa)
-    for (int pb = 0; pb <= pa; ++pb) {
-      ProjTable* q = &pt[(size_t)quartet_class(pa, pb) * 4];
-      q[0] = per_l[PC_LA[pa]]; q[1] = per_l[PC_LB[pa]]; q[2] = per_l[PC_LA[pb]]; q[3] = per_l[PC_LB[pb]];
-    }
-  if ((rc = upload(ctx, ctx->d_proj, pt))) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->have_basis = true;
   ctx->have_cutoff = ctx->have_screen = false;
@@ -1252,10 +1200,9 @@ int oqpb_eri_block(oqpb_ctx* ctx, int i, int j, int k, int l, double* out, int* 
   A.ntasks = d_cnt.as<unsigned>();
   A.counter = d_cnt.as<unsigned>() + 1;
   A.prim_cutoff = ctx->cut.pair * ctx->cut.pair;
-  A.proj = proj_for(ctx, pc_of(pca), pc_of(pcb));
   A.mode = MODE_BLOCK;
   A.blockout = d_out.as<double>();
-  const ClassEntry& ce = class_table()[quartet_class(pc_of(pca), pc_of(pcb))];
+  const ClassEntry& ce = class_table(ctx->pure_l[2] | (ctx->pure_l[3] << 1))[quartet_class(pc_of(pca), pc_of(pcb))];
   CK(ce.launch(A, 1, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   // kernel block order: (A,B,C,D) = (bra.sa, bra.sb, ket.sa, ket.sb); map back to the caller's (i,j,k,l)
