@@ -117,12 +117,13 @@ struct Cart {
   __host__ __device__ static constexpr int z(int c) { return L - x(c) - y(c); }
 };
 
+template <int I, class F, int... Is>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, Is...>) {
+  (f(std::integral_constant<int, I + Is>{}), ...);
+}
 template <int I, int N, class F>
 __device__ __forceinline__ void static_for(F&& f) {
-  if constexpr (I < N) {
-    f(std::integral_constant<int, I>{});
-    static_for<I + 1, N>(f);
-  }
+  static_for_impl<I>(f, std::make_integer_sequence<int, (N > I ? N - I : 0)>{});
 }
 
 __device__ __forceinline__ void cart_xyz_rt(int l, int c, int& x, int& y, int& z) {
@@ -916,7 +917,7 @@ constexpr int SMALL_MAX = 36;
 // Medium classes (SMALL_MAX < NCART4 <= MEDIUM_MAX): same one-thread-per-quartet kernel, but the finished
 // gx/gy/gz tables of a root live in shared memory (column per thread, [entry][thread]: conflict-free) so the
 // registers are left to the NCART4 accumulators.
-constexpr int MEDIUM_MAX = 100;
+constexpr int MEDIUM_MAX = 150;
 constexpr int SMALL_NT = 128, MEDIUM_NT = 64;
 
 // Rys evaluation state at X shared by all roots and weights of a primitive quartet
@@ -931,27 +932,43 @@ __device__ __forceinline__ RysX rys_prepare(const EriArgs& a, double X) {
   s.iv = 0;
   s.rx = s.rs = s.t = 0.0;
   if (s.asym) {
-    s.rx = 1.0 / X;  // half-range Gauss-Hermite asymptote (rys.F90:2711-2713)
-    s.rs = sqrt(s.rx);
+    s.rs = rsqrt(X);  // half-range Gauss-Hermite asymptote (rys.F90:2711-2713): r = h_r / X, w = h_w / sqrt(X)
+    s.rx = s.rs * s.rs;
   } else {
     s.iv = (int)X;
     s.t = 2.0 * (X - (double)s.iv) - 1.0;
   }
   return s;
 }
-// root r (as t^2) and its weight: two interleaved Clenshaw recurrences over 16-byte table loads
+// Chebyshev table of one nroots in shared memory: per unit interval 2R functions x 12 coefficients, padded by
+// 2 doubles so that the 16-byte reads of lanes in different intervals fall into different banks
 template <int R>
-__device__ __forceinline__ void rys_pair(const EriArgs& a, const RysX& s, int r, double& t2, double& w) {
+struct RysSmem {
+  static constexpr int STRIDE = 24 * R + 2;
+  static constexpr bool USE = R <= 3;
+  __host__ __device__ static constexpr int doubles(int xmax) { return xmax * STRIDE; }
+};
+// root r (as t^2) and its weight: two interleaved Clenshaw recurrences over 16-byte table loads
+template <int R, bool SM>
+__device__ __forceinline__ void rys_pair(const EriArgs& a, const double* __restrict__ stab, const RysX& s, int r,
+                                         double& t2, double& w) {
   if (s.asym) {
     t2 = a.herm_r[r] * s.rx;
     w = a.herm_w[r] * s.rs;
     return;
   }
-  const double2* __restrict__ ct = reinterpret_cast<const double2*>(a.rys_tab + ((size_t)s.iv * (2 * R) + r) * 12);
-  const double2* __restrict__ cw = ct + 6 * R;
   double2 p[6], q[6];
+  if constexpr (SM) {
+    const double2* ct = reinterpret_cast<const double2*>(stab + s.iv * RysSmem<R>::STRIDE + r * 12);
+    const double2* cw = ct + 6 * R;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) { p[k] = __ldg(ct + k); q[k] = __ldg(cw + k); }
+    for (int k = 0; k < 6; ++k) { p[k] = ct[k]; q[k] = cw[k]; }
+  } else {
+    const double2* __restrict__ ct = reinterpret_cast<const double2*>(a.rys_tab + ((size_t)s.iv * (2 * R) + r) * 12);
+    const double2* __restrict__ cw = ct + 6 * R;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { p[k] = __ldg(ct + k); q[k] = __ldg(cw + k); }
+  }
   const double x2 = 2.0 * s.t;
   double b1 = 0.0, b2 = 0.0, e1 = 0.0, e2 = 0.0;
 #pragma unroll
@@ -979,6 +996,12 @@ eri_small_kernel(const EriArgs A) {
   constexpr int NTOT = N0 * N1 * N2 * N3;
   const unsigned ntasks = *A.ntasks;
   unsigned long long st_prim = 0, st_ints = 0;
+  constexpr bool RSM = !GS && RysSmem<R>::USE;  // Rys table of this nroots staged in shared memory
+  if constexpr (RSM) {
+    const int nint = A.rys_xmax;
+    for (int i = threadIdx.x; i < nint * 24 * R; i += NTH) gsm[(i / (24 * R)) * RysSmem<R>::STRIDE + i % (24 * R)] = A.rys_tab[i];
+    __syncthreads();
+  }
   for (unsigned ti = blockIdx.x * blockDim.x + threadIdx.x; ti < ntasks; ti += gridDim.x * blockDim.x) {
     const int2 tk = A.tasks[ti];
     const PairEntry pb = A.bra[tk.x], pk = A.ket[tk.y];
@@ -1010,19 +1033,20 @@ eri_small_kernel(const EriArgs A) {
         const double Px = p01.x, Py = p01.y, Pz = p23.x;
         any = true;
         ++st_prim;
-        const double abinv = 1.0 / ab;
+        const double rsab = rsqrt(ab);
+        const double abinv = rsab * rsab;
         const double rho = zeta * eta * abinv;
         const double PQ[3] = {Px - Qx, Py - Qy, Pz - Qz};
         const double PA[3] = {Px - Ax, Py - Ay, Pz - Az};
         const double QC[3] = {Qx - Cx, Qy - Cy, Qz - Cz};
         const double X = rho * (PQ[0] * PQ[0] + PQ[1] * PQ[1] + PQ[2] * PQ[2]);
-        const double pref = pfac * sqrt(abinv);
+        const double pref = pfac * rsab;
         const double rz = rho * zinv, re = rho * einv, hz = 0.5 * zinv, he = 0.5 * einv;
         const RysX rx = rys_prepare(A, X);
 #pragma unroll 1
         for (int r = 0; r < R; ++r) {
           double t2, w;
-          rys_pair<R>(A, rx, r, t2, w);
+          rys_pair<R, RSM>(A, gsm, rx, r, t2, w);
           const double b10 = hz * (1.0 - t2 * rz), b01 = he * (1.0 - t2 * re), b00 = 0.5 * t2 * abinv;
           constexpr int G3 = NIJ1 * NKL1;
           double g[GS ? 1 : 3][GS ? 1 : G3];
@@ -1460,7 +1484,9 @@ template <int LA, int LB, int LC, int LD, int PV>
 cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
   using Cfg = ClassCfg<LA, LB, LC, LD>;
   if constexpr (Cfg::NCART4 <= SMALL_MAX) {
-    eri_small_kernel<LA, LB, LC, LD, PV, false><<<nblocks, SMALL_NT, 0, st>>>(args);
+    constexpr int R = Cfg::R;
+    const size_t smem = RysSmem<R>::USE ? (size_t)RysSmem<R>::doubles(args.rys_xmax) * sizeof(double) : 0;
+    eri_small_kernel<LA, LB, LC, LD, PV, false><<<nblocks, SMALL_NT, smem, st>>>(args);
     return cudaGetLastError();
   } else if constexpr (Cfg::NCART4 <= MEDIUM_MAX) {
     constexpr size_t smem = (size_t)3 * Cfg::NIJ1 * Cfg::NKL1 * MEDIUM_NT * sizeof(double);

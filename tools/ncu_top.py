@@ -6,6 +6,14 @@ import csv, io, subprocess, sys
 wl = sys.argv[1]
 pairs = list(zip(sys.argv[2::2], sys.argv[3::2]))
 for out, rx in pairs:
+    if "@" in out:  # <out-name>@<N>: capture the N-th matching launch, no duration pass
+        out, best = out.split("@"); best = int(best)
+        cmd = ["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on", "--kernel-name-base", "demangled",
+               "-k", f"regex:{rx}", "--launch-skip", str(best), "-c", "1", "-o", f"gpurun_out/{out}", "-f",
+               "python", "tools/scratch/g4.py", wl, "1"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        print(out, r.stdout[-200:], flush=True)
+        continue
     cmd = ["ncu", "--metrics", "gpu__time_duration.sum", "--clock-control", "none", "--kernel-name-base", "demangled",
            "-k", f"regex:{rx}", "--csv", "python", "tools/scratch/g4.py", wl, "1"]
     r = subprocess.run(cmd, capture_output=True, text=True)
