@@ -137,7 +137,12 @@ struct oqpb_ctx {
   std::vector<double> Qmat;  // nshell x nshell (host)
   DevBuf d_Qmat, d_dsh, d_maxden, d_ok, d_d4, d_rowsbuf;
   // work
-  DevBuf d_tasks, d_counters, d_Dsq, d_F, d_Din, d_stats, d_gen_in, d_gen_out;
+  static constexpr int NSTREAM = 4;  // launch lanes: chunk c runs on lane c % NSTREAM (own task buffer) so that the
+                                     // tail of one class kernel overlaps the next enumeration / class kernel
+  DevBuf d_tasks[NSTREAM], d_counters, d_Dsq, d_F, d_Din, d_stats, d_gen_in, d_gen_out;
+  cudaStream_t lane[NSTREAM] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t lane_ev[NSTREAM] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork_ev = nullptr;
   size_t task_cap = (size_t)1 << 23;
   int rank = 0, nranks = 1;
   // stats of the last build
@@ -696,7 +701,8 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   CK(ctx->d_counters.ensure((3 * nch + 4) * sizeof(unsigned long long)));
   CK(cudaMemsetAsync(ctx->d_counters.p, 0, (3 * nch + 4) * sizeof(unsigned long long), ctx->stream));
   unsigned* d_cnt = ctx->d_counters.as<unsigned>();  // [2*c] = ntasks, [2*c+1] = fetch counter
-  CK(ctx->d_tasks.ensure(ctx->task_cap * sizeof(int2)));
+  const int nlane = ctx->profile || ctx->record ? 1 : oqpb_ctx::NSTREAM;
+  for (int l = 0; l < nlane; ++l) CK(ctx->d_tasks[l].ensure(ctx->task_cap * sizeof(int2)));
   CK(ctx->d_stats.ensure((2 * nch + 2) * sizeof(unsigned long long)));
   CK(cudaMemsetAsync(ctx->d_stats.p, 0, (2 * nch + 2) * sizeof(unsigned long long), ctx->stream));
   std::vector<unsigned long long> h_stats(2 * nch + 2, 0);
@@ -713,23 +719,30 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     enum_attr = true;
   }
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  if (nlane > 1) {
+    CK(cudaEventRecord(ctx->fork_ev, ctx->stream));
+    for (int l = 0; l < nlane; ++l) CK(cudaStreamWaitEvent(ctx->lane[l], ctx->fork_ev, 0));
+  }
   for (size_t c = 0; c < nch; ++c) {
     const Chunk& ch = chunks[c];
+    const int ln = (int)(c % nlane);
+    cudaStream_t cs = nlane > 1 ? ctx->lane[ln] : ctx->stream;
+    int2* d_tasks = ctx->d_tasks[ln].as<int2>();
     size_t ci = cp_index(ch.pca, ch.pcb);
     int offa = T.cls_off[ch.pca], offb = T.cls_off[ch.pcb];
     int nbra = (ch.p1 - ch.p0 + nr - 1) / nr + 1;
     // first bra of this rank at or after p0
     int pstart = ch.p0 + ((rk - ch.p0 % nr) % nr + nr) % nr;
-    k_enum<<<nbra, 256, use_smem ? smem_rows : 0, ctx->stream>>>(
+    k_enum<<<nbra, 256, use_smem ? smem_rows : 0, cs>>>(
         T.d_ent.as<PairEntry>() + offa, T.d_ent.as<PairEntry>() + offb, T.d_Q.as<double>() + offa,
         T.d_Q.as<double>() + offb, ctx->d_d4.as<double>() + offa, ctx->d_d4.as<double>() + offb,
         ctx->d_ok.as<int>() + offa, ctx->d_ok.as<int>() + offb, T.d_canon.as<int>() + offa,
         T.d_canon.as<int>() + offb, d_km.as<int>() + km_off[ci], pstart, ch.p1, nr, ch.pca == ch.pcb,
-        ctx->d_dsh.as<double>(), ns, cutoff, ctx->d_tasks.as<int2>(), d_cnt + 2 * c, (unsigned)ctx->task_cap, use_smem);
+        ctx->d_dsh.as<double>(), ns, cutoff, d_tasks, d_cnt + 2 * c, (unsigned)ctx->task_cap, use_smem);
     CK(cudaGetLastError());
     EriArgs A;
     fill_common_args(ctx, T, ch.pca, ch.pcb, A);
-    A.tasks = ctx->d_tasks.as<int2>();
+    A.tasks = d_tasks;
     A.ntasks = d_cnt + 2 * c;
     A.counter = d_cnt + 2 * c + 1;
     A.prim_cutoff = ctx->cut.pair * ctx->cut.pair;
@@ -744,10 +757,10 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     const ClassEntry& ce = tab[qcls];
     size_t nb = std::min<size_t>((ch.cand + ce.qpb - 1) / ce.qpb, (size_t)148 * 32);
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
-    if (ctx->profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, ctx->stream); }
-    CK(ce.launch(A, (int)std::max<size_t>(nb, 1), ctx->stream));
+    if (ctx->profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, cs); }
+    CK(ce.launch(A, (int)std::max<size_t>(nb, 1), cs));
     if (ctx->profile) {
-      cudaEventRecord(pe1, ctx->stream);
+      cudaEventRecord(pe1, cs);
       cudaEventSynchronize(pe1);
       float pms = 0;
       cudaEventElapsedTime(&pms, pe0, pe1);
@@ -761,7 +774,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
       CK(cudaMemcpyAsync(&n, d_cnt + 2 * c, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
       rec_tmp.resize(n);
-      CK(cudaMemcpy(rec_tmp.data(), ctx->d_tasks.p, n * sizeof(int2), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(rec_tmp.data(), d_tasks, n * sizeof(int2), cudaMemcpyDeviceToHost));
       for (unsigned k = 0; k < n; ++k) {
         const PairEntry& eb = T.ent[offa + rec_tmp[k].x];
         const PairEntry& ek = T.ent[offb + rec_tmp[k].y];
@@ -769,6 +782,12 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
         if ((long)i * (i + 1) / 2 + j < (long)kk * (kk + 1) / 2 + l) { std::swap(i, kk); std::swap(j, l); }
         ctx->rec.push_back(i); ctx->rec.push_back(j); ctx->rec.push_back(kk); ctx->rec.push_back(l);
       }
+    }
+  }
+  if (nlane > 1) {
+    for (int l = 0; l < nlane; ++l) {
+      CK(cudaEventRecord(ctx->lane_ev[l], ctx->lane[l]));
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->lane_ev[l], 0));
     }
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -840,6 +859,11 @@ int oqpb_ctx_create(oqpb_ctx** out, int device) {
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return OQPB_ERR_CUDA; }
   cudaEventCreate(&ctx->ev0);
   cudaEventCreate(&ctx->ev1);
+  cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
+  for (int l = 0; l < oqpb_ctx::NSTREAM; ++l) {
+    cudaStreamCreateWithFlags(&ctx->lane[l], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->lane_ev[l], cudaEventDisableTiming);
+  }
   // Rys tables
   if (ctx->d_rys.ensure(sizeof(RYS_TAB_H)) != cudaSuccess) { delete ctx; return OQPB_ERR_CUDA; }
   cudaMemcpy(ctx->d_rys.p, RYS_TAB_H, sizeof(RYS_TAB_H), cudaMemcpyHostToDevice);
@@ -855,12 +879,14 @@ void oqpb_ctx_destroy(oqpb_ctx* ctx) {
   free_pairtable(ctx->run);
   for (DevBuf* b : {&ctx->d_am, &ctx->d_ncontr, &ctx->d_goff, &ctx->d_aooff, &ctx->d_naos, &ctx->d_ex, &ctx->d_cc,
                     &ctx->d_xyz, &ctx->d_rys, &ctx->d_Qmat, &ctx->d_dsh, &ctx->d_maxden, &ctx->d_ok,
-                    &ctx->d_d4, &ctx->d_rowsbuf, &ctx->d_tasks, &ctx->d_counters, &ctx->d_Dsq, &ctx->d_F, &ctx->d_Din,
+                    &ctx->d_d4, &ctx->d_rowsbuf, &ctx->d_tasks[0], &ctx->d_tasks[1], &ctx->d_tasks[2], &ctx->d_tasks[3], &ctx->d_counters, &ctx->d_Dsq, &ctx->d_F, &ctx->d_Din,
                     &ctx->d_stats, &ctx->d_gen_in, &ctx->d_gen_out})
     b->release();
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->fork_ev);
+  for (int l = 0; l < oqpb_ctx::NSTREAM; ++l) { cudaStreamDestroy(ctx->lane[l]); cudaEventDestroy(ctx->lane_ev[l]); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
