@@ -1181,7 +1181,11 @@ struct GroupCfg {
   static constexpr int G = acc_for(4) <= LIMIT ? 4 : (acc_for(8) <= LIMIT ? 8 : (acc_for(16) <= LIMIT ? 16 : 32));
   static constexpr int NVL = (VL + G - 1) / G;
   static constexpr int QPW = 32 / G;
-  static constexpr int QBYTES = C::QSM * 8 + 96 + 128;  // block/g region + QInfo + primitive list
+  // per-quartet stride in doubles: == G (mod 16) for G < 16, so that the 16 lanes of a half-warp (16/G quartets x G
+  // lanes, lane stride odd) fall into 16 different 8-byte banks
+  static constexpr int QSMG = G >= 16 ? C::QSM : ((C::QSM + 15 - G) / 16) * 16 + G;
+  static_assert(QSMG >= C::QSM, "QSMG");
+  static constexpr int QBYTES = QSMG * 8 + 96 + 128;  // block/g region + QInfo + primitive list
   static constexpr int WPC = (2 * QPW * QBYTES <= 64 * 1024) ? 2 : 1;
   static constexpr int NT = 32 * WPC;
   static constexpr size_t SMEM = (size_t)WPC * QPW * QBYTES;
@@ -1196,7 +1200,7 @@ eri_group_kernel(const EriArgs A) {
   using GC = GroupCfg<LA, LB, LC, LD>;
   constexpr int R = Cfg::R, NA = Cfg::NA, NB = Cfg::NB, NC = Cfg::NC, ND = Cfg::ND, NKET = Cfg::NKET;
   constexpr int NMAX = Cfg::NMAX, MMAX = Cfg::MMAX, NKL1 = Cfg::NKL1;
-  constexpr int G1 = Cfg::G1, G2 = Cfg::G2, GSTR = Cfg::GSTR, QSM = Cfg::QSM;
+  constexpr int G1 = Cfg::G1, G2 = Cfg::G2, GSTR = Cfg::GSTR, QSM = GC::QSMG;
   constexpr int G = GC::G, NVL = GC::NVL, QPW = GC::QPW, VL = GC::VL;
   constexpr int LCAP = 64;
   constexpr unsigned FULL = 0xffffffffu;
