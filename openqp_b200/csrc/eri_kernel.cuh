@@ -258,10 +258,42 @@ __device__ __forceinline__ unsigned tri_u(unsigned p, unsigned q) {  // nbf <= 4
 // MODE_SYM: the reference's six packed updates (int2.F90:1414-1484 / 1488-1578) on the full block
 // with the shell-level coincidence factor already applied (equivalent to the unique-AO walk + AO-level halving
 // of storeints, int2.F90:1769-1851).  One FP64 red per Fock element per quartet.
+// Warp-segmented reduction for the thread-per-quartet kernels.  The enumeration writes the surviving kets of a bra
+// contiguously and the pair lists are ordered by the ket's first shell inside a Schwarz bin, so the 32 quartets of
+// a warp form runs with the same bra (same J_ab targets) and, inside those, runs with the same ket shell c (same
+// K_ac / K_bc targets).  A run is summed with shuffles and its first lane issues the one red.global.add.
+struct SegMask {
+  unsigned char up[5];  // lane + 2^k belongs to the same run
+  bool head;            // first lane of its run
+};
+__device__ __forceinline__ SegMask seg_make(long long key, int lane) {
+  SegMask m;
+  const long long prev = __shfl_up_sync(0xffffffffu, key, 1);
+  m.head = lane == 0 || prev != key;
+  // run index = number of heads at or before this lane: equal keys that are not adjacent stay separate runs
+  const unsigned heads = __ballot_sync(0xffffffffu, m.head);
+  const int rid = __popc(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int o = __shfl_down_sync(0xffffffffu, rid, 1 << k);
+    m.up[k] = (lane + (1 << k) < 32) && o == rid;
+  }
+  return m;
+}
+__device__ __forceinline__ double seg_sum(double v, const SegMask& m) {
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const double o = __shfl_down_sync(0xffffffffu, v, 1 << k);
+    if (m.up[k]) v += o;
+  }
+  return v;  // run total in the head lane
+}
+
 // (1) block in registers, one thread: everything unrolled, the density sub-block of a pass is loaded first
-template <int N0, int N1, int N2, int N3>
+// All 32 lanes of the warp must call this together (lanes without a quartet pass a zero block).
+template <int N0, int N1, int N2, int N3, bool SEGC>
 __device__ __forceinline__ void digest_sym_reg(const EriArgs& A, const double (&v)[N0 * N1 * N2 * N3], int o0, int o1,
-                                               int o2, int o3) {
+                                               int o2, int o3, const SegMask& mbra, const SegMask& mc) {
   const unsigned nbf = (unsigned)A.nbf;
   const double c4 = 4.0 * A.cj, c1 = A.ck;
 #define VV(a, b, c, d) v[(((a)*N1 + (b)) * N2 + (c)) * N3 + (d)]
@@ -284,7 +316,8 @@ __device__ __forceinline__ void digest_sym_reg(const EriArgs& A, const double (&
           for (int c = 0; c < N2; ++c)
 #pragma unroll
             for (int d = 0; d < N3; ++d) sum = fma(VV(a, b, c, d), dd[c * N3 + d], sum);
-          if (sum != 0.0) atomicAdd(F + tri_u(o0 + a, o1 + b), c4 * sum);
+          sum = seg_sum(sum, mbra);
+          if (mbra.head && sum != 0.0) atomicAdd(F + tri_u(o0 + a, o1 + b), c4 * sum);
         }
     }
     {  // J_cd += 4 cj sum_ab v D_ab
@@ -320,7 +353,8 @@ __device__ __forceinline__ void digest_sym_reg(const EriArgs& A, const double (&
           for (int b = 0; b < N1; ++b)
 #pragma unroll
             for (int d = 0; d < N3; ++d) sum = fma(VV(a, b, c, d), dd[b * N3 + d], sum);
-          if (sum != 0.0) atomicAdd(F + tri_u(o0 + a, o2 + c), -c1 * sum);
+          if constexpr (SEGC) sum = seg_sum(sum, mc);
+          if ((!SEGC || mc.head) && sum != 0.0) atomicAdd(F + tri_u(o0 + a, o2 + c), -c1 * sum);
         }
     }
     {  // K_ad -= ck sum_bc v D_bc
@@ -356,7 +390,8 @@ __device__ __forceinline__ void digest_sym_reg(const EriArgs& A, const double (&
           for (int a = 0; a < N0; ++a)
 #pragma unroll
             for (int d = 0; d < N3; ++d) sum = fma(VV(a, b, c, d), dd[a * N3 + d], sum);
-          if (sum != 0.0) atomicAdd(F + tri_u(o1 + b, o2 + c), -c1 * sum);
+          if constexpr (SEGC) sum = seg_sum(sum, mc);
+          if ((!SEGC || mc.head) && sum != 0.0) atomicAdd(F + tri_u(o1 + b, o2 + c), -c1 * sum);
         }
     }
     {  // K_bd -= ck sum_ac v D_ac
@@ -468,6 +503,160 @@ __device__ __forceinline__ void digest_sym(const EriArgs& A, const double* blk, 
         for (int c = 0; c < N2; ++c) sum = fma(v[c * N3], __ldg(drow + c), sum);
       }
       if (sum != 0.0) atomicAdd(F + tri_u(o1 + b, o3 + d), -c1 * sum);
+    }
+  }
+}
+
+// (3) group kernel: block in shared memory, a quartet is owned by G lanes and a warp holds 32/G quartets.  Same
+// updates as (2); J_ab and the K_ac / K_bc sums of quartets of the warp that share the bra (and the ket shell c)
+// are first added across the quartet slots with shuffles (stride G), so that one lane issues the red.
+template <int G>
+struct GroupSeg {
+  static constexpr int QPW = 32 / G;
+  static constexpr int NST = QPW == 1 ? 0 : (QPW == 2 ? 1 : (QPW == 4 ? 2 : 3));
+  bool up[NST > 0 ? NST : 1];
+  bool head;
+};
+template <int G>
+__device__ __forceinline__ GroupSeg<G> gseg_make(long long key, int lane) {
+  GroupSeg<G> m;
+  m.head = true;
+  if constexpr (GroupSeg<G>::NST > 0) {
+    const int g = lane / G;
+    const long long prev = __shfl_up_sync(0xffffffffu, key, G);
+    m.head = g == 0 || prev != key;
+    const unsigned heads = __ballot_sync(0xffffffffu, m.head && (lane % G) == 0);
+    const int rid = __popc(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+    for (int k = 0; k < GroupSeg<G>::NST; ++k) {
+      const int o = __shfl_down_sync(0xffffffffu, rid, G << k);
+      m.up[k] = (g + (1 << k) < GroupSeg<G>::QPW) && o == rid;
+    }
+  }
+  return m;
+}
+template <int G>
+__device__ __forceinline__ double gseg_sum(double v, const GroupSeg<G>& m) {
+  if constexpr (GroupSeg<G>::NST > 0) {
+#pragma unroll
+    for (int k = 0; k < GroupSeg<G>::NST; ++k) {
+      const double o = __shfl_down_sync(0xffffffffu, v, G << k);
+      if (m.up[k]) v += o;
+    }
+  }
+  return v;
+}
+// all 32 lanes call this together; `work` = this lane's quartet has a non-zero block
+template <int N0, int N1, int N2, int N3, int G>
+__device__ __forceinline__ void digest_sym_group(const EriArgs& A, const double* blk, int o0, int o1, int o2, int o3,
+                                                 int t, bool work, const GroupSeg<G>& mbra, const GroupSeg<G>& mc) {
+  const unsigned nbf = (unsigned)A.nbf;
+  constexpr int N23 = N2 * N3;
+  const double c4 = 4.0 * A.cj, c1 = A.ck;
+  for (int m = 0; m < A.nmat; ++m) {
+    const double* __restrict__ DJ = A.DJ[m];
+    const double* __restrict__ DK = A.DK[m];
+    double* __restrict__ F = A.F[m];
+    // J_ab += 4 cj sum_cd v D_cd
+    for (int ob = 0; ob < N0 * N1; ob += G) {
+      const int o = ob + t;
+      const bool act = work && o < N0 * N1;
+      const int a = o / N1, b = o % N1;
+      double sum = 0.0;
+      if (act) {
+        const double* v = blk + o * N23;
+#pragma unroll
+        for (int c = 0; c < N2; ++c) {
+          const double* drow = DJ + ((unsigned)(o2 + c) * nbf + (unsigned)o3);
+#pragma unroll
+          for (int d = 0; d < N3; ++d) sum = fma(v[c * N3 + d], __ldg(drow + d), sum);
+        }
+      }
+      sum = gseg_sum<G>(sum, mbra);
+      if (act && mbra.head && sum != 0.0) atomicAdd(F + tri_u(o0 + a, o1 + b), c4 * sum);
+    }
+    // J_cd += 4 cj sum_ab v D_ab
+    for (int ob = 0; ob < N23; ob += G) {
+      const int o = ob + t;
+      if (work && o < N23) {
+        const int c = o / N3, d = o % N3;
+        double sum = 0.0;
+#pragma unroll
+        for (int a = 0; a < N0; ++a) {
+          const double* drow = DJ + ((unsigned)(o0 + a) * nbf + (unsigned)o1);
+#pragma unroll
+          for (int b = 0; b < N1; ++b) sum = fma(blk[(a * N1 + b) * N23 + o], __ldg(drow + b), sum);
+        }
+        if (sum != 0.0) atomicAdd(F + tri_u(o2 + c, o3 + d), c4 * sum);
+      }
+    }
+    // K_ac -= ck sum_bd v D_bd
+    for (int ob = 0; ob < N0 * N2; ob += G) {
+      const int o = ob + t;
+      const bool act = work && o < N0 * N2;
+      const int a = o / N2, c = o % N2;
+      double sum = 0.0;
+      if (act) {
+#pragma unroll
+        for (int b = 0; b < N1; ++b) {
+          const double* drow = DK + ((unsigned)(o1 + b) * nbf + (unsigned)o3);
+          const double* v = blk + (a * N1 + b) * N23 + c * N3;
+#pragma unroll
+          for (int d = 0; d < N3; ++d) sum = fma(v[d], __ldg(drow + d), sum);
+        }
+      }
+      sum = gseg_sum<G>(sum, mc);
+      if (act && mc.head && sum != 0.0) atomicAdd(F + tri_u(o0 + a, o2 + c), -c1 * sum);
+    }
+    // K_ad -= ck sum_bc v D_bc
+    for (int ob = 0; ob < N0 * N3; ob += G) {
+      const int o = ob + t;
+      if (work && o < N0 * N3) {
+        const int a = o / N3, d = o % N3;
+        double sum = 0.0;
+#pragma unroll
+        for (int b = 0; b < N1; ++b) {
+          const double* drow = DK + ((unsigned)(o1 + b) * nbf + (unsigned)o2);
+          const double* v = blk + (a * N1 + b) * N23 + d;
+#pragma unroll
+          for (int c = 0; c < N2; ++c) sum = fma(v[c * N3], __ldg(drow + c), sum);
+        }
+        if (sum != 0.0) atomicAdd(F + tri_u(o0 + a, o3 + d), -c1 * sum);
+      }
+    }
+    // K_bc -= ck sum_ad v D_ad
+    for (int ob = 0; ob < N1 * N2; ob += G) {
+      const int o = ob + t;
+      const bool act = work && o < N1 * N2;
+      const int b = o / N2, c = o % N2;
+      double sum = 0.0;
+      if (act) {
+#pragma unroll
+        for (int a = 0; a < N0; ++a) {
+          const double* drow = DK + ((unsigned)(o0 + a) * nbf + (unsigned)o3);
+          const double* v = blk + (a * N1 + b) * N23 + c * N3;
+#pragma unroll
+          for (int d = 0; d < N3; ++d) sum = fma(v[d], __ldg(drow + d), sum);
+        }
+      }
+      sum = gseg_sum<G>(sum, mc);
+      if (act && mc.head && sum != 0.0) atomicAdd(F + tri_u(o1 + b, o2 + c), -c1 * sum);
+    }
+    // K_bd -= ck sum_ac v D_ac
+    for (int ob = 0; ob < N1 * N3; ob += G) {
+      const int o = ob + t;
+      if (work && o < N1 * N3) {
+        const int b = o / N3, d = o % N3;
+        double sum = 0.0;
+#pragma unroll
+        for (int a = 0; a < N0; ++a) {
+          const double* drow = DK + ((unsigned)(o0 + a) * nbf + (unsigned)o2);
+          const double* v = blk + (a * N1 + b) * N23 + d;
+#pragma unroll
+          for (int c = 0; c < N2; ++c) sum = fma(v[c * N3], __ldg(drow + c), sum);
+        }
+        if (sum != 0.0) atomicAdd(F + tri_u(o1 + b, o3 + d), -c1 * sum);
+      }
     }
   }
 }
@@ -1002,9 +1191,14 @@ eri_small_kernel(const EriArgs A) {
     for (int i = threadIdx.x; i < nint * 24 * R; i += NTH) gsm[(i / (24 * R)) * RysSmem<R>::STRIDE + i % (24 * R)] = A.rys_tab[i];
     __syncthreads();
   }
-  for (unsigned ti = blockIdx.x * blockDim.x + threadIdx.x; ti < ntasks; ti += gridDim.x * blockDim.x) {
-    const int2 tk = A.tasks[ti];
-    const PairEntry pb = A.bra[tk.x], pk = A.ket[tk.y];
+  const int lane = threadIdx.x & 31;
+  // warp-uniform trip count: the digestion reduces across the lanes of a warp
+  for (unsigned tb = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); tb < ntasks; tb += gridDim.x * blockDim.x) {
+    const unsigned ti = tb + lane;
+    const bool valid = ti < ntasks;
+    const int2 tk = A.tasks[valid ? ti : ntasks - 1];
+    PairEntry pb = A.bra[tk.x], pk = A.ket[tk.y];
+    if (!valid) pb.pcnt = pk.pcnt = 0;  // no primitive work, zero block
     const double Ax = pb.ax, Ay = pb.ay, Az = pb.az, Cx = pk.ax, Cy = pk.ay, Cz = pk.az;
     const double AB[3] = {pb.abx, pb.aby, pb.abz};
     const double CD[3] = {pk.abx, pk.aby, pk.abz};
@@ -1109,9 +1303,9 @@ eri_small_kernel(const EriArgs A) {
         }
       }
     }
-    if (!any) {
-      if (A.mode == MODE_SCHWARZ) A.qout[tk.x] = 0.0;
-      if (A.mode == MODE_BLOCK)
+    if (A.mode != MODE_SYM && !any) {  // (mode is uniform; MODE_SYM keeps the warp together for the reductions)
+      if (valid && A.mode == MODE_SCHWARZ) A.qout[tk.x] = 0.0;
+      if (valid && A.mode == MODE_BLOCK)
         for (int e = 0; e < NTOT; ++e) A.blockout[e] = 0.0;
       continue;
     }
@@ -1125,12 +1319,14 @@ eri_small_kernel(const EriArgs A) {
       double mx = 0.0;
 #pragma unroll
       for (int e = 0; e < NTOT; ++e) mx = fmax(mx, fabs(blk[e]));
-      A.qout[tk.x] = sqrt(mx);
+      if (valid) A.qout[tk.x] = sqrt(mx);
       continue;
     }
     if (A.mode == MODE_BLOCK) {
+      if (valid) {
 #pragma unroll
-      for (int e = 0; e < NTOT; ++e) A.blockout[e] = blk[e];
+        for (int e = 0; e < NTOT; ++e) A.blockout[e] = blk[e];
+      }
       continue;
     }
     // element cutoff (int2.F90:1806-1812) and shell-level coincidence factor (int2.F90:1849-1851)
@@ -1149,8 +1345,12 @@ eri_small_kernel(const EriArgs A) {
     }
     st_ints += (unsigned long long)nz * (unsigned)(8.0f * facf);
     if (A.mode == MODE_SYM) {
-      digest_sym_reg<N0, N1, N2, N3>(A, blk, pb.oa, pb.ob, pk.oa, pk.ob);
-    } else {
+      // runs of equal bra / equal (bra, ket shell c) inside the warp; lanes without a quartet get unique keys
+      const long long kbra = valid ? (long long)tk.x : -1 - (long long)lane;
+      const SegMask mbra = seg_make(kbra, lane);
+      const SegMask mc = seg_make(valid ? ((long long)tk.x << 20) | (long long)pk.sa : kbra, lane);
+      digest_sym_reg<N0, N1, N2, N3, !GS>(A, blk, pb.oa, pb.ob, pk.oa, pk.ob, mbra, mc);
+    } else if (valid) {
       double loc[NTOT];
 #pragma unroll
       for (int e = 0; e < NTOT; ++e) loc[e] = blk[e];
@@ -1473,9 +1673,14 @@ eri_group_kernel(const EriArgs A) {
       st_ints += (unsigned long long)nz * (unsigned)(8.0f * qi.fac);
     }
     __syncwarp();
-    if (work) {
-      if (A.mode == MODE_SYM) digest_sym<N0, N1, N2, N3>(A, src, qi.oa, qi.ob, qi.oc, qi.od, t, G);
-      else digest_gen<N0, N1, N2, N3>(A, src, qi.oa, qi.ob, qi.oc, qi.od, t, G);
+    if (A.mode == MODE_SYM) {
+      // quartets of the warp with the same bra / the same (bra, ket shell c) are summed before the red
+      const long long kbra = valid ? (long long)qi.bra_id : -1 - (long long)g;
+      const GroupSeg<G> mbra = gseg_make<G>(kbra, lane);
+      const GroupSeg<G> mc = gseg_make<G>(valid ? ((long long)qi.bra_id << 20) | (long long)qi.sc : kbra, lane);
+      digest_sym_group<N0, N1, N2, N3, G>(A, src, qi.oa, qi.ob, qi.oc, qi.od, t, work, mbra, mc);
+    } else if (work) {
+      digest_gen<N0, N1, N2, N3>(A, src, qi.oa, qi.ob, qi.oc, qi.od, t, G);
     }
   }
   if (A.stat) {

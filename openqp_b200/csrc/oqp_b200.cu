@@ -85,6 +85,7 @@ struct PairTable {
   std::vector<PairEntry> ent;
   std::vector<int> canon;  // canonical pair id tri(i,j), i>=j by shell index
   std::vector<double> Q;
+  std::vector<double> Qsuf;  // per list: max of Q over the entries at or after this one
   int cls_off[NL + 1] = {0};  // offsets of the NL pair lists (class-major, bucket-minor)
   DevBuf d_ent, d_prim, d_Q, d_canon;
   long nprim = 0;
@@ -303,16 +304,23 @@ __global__ void k_entry_screen(long nent, const PairEntry* __restrict__ ent, con
   d4[e] = 4.0 * dsh[(size_t)ent[e].sa * nshell + ent[e].sb];
 }
 
-// Quartet enumeration for one (bra class, ket class) chunk: CTA per bra entry, threads over ket entries.
+// Quartet enumeration for one (bra list, ket list) chunk: CTA per bra entry, threads over ket entries.
 // Predicate = screen_ijkl, int2.F90:975-986, evaluated in the reference's operation order without FMA.
-// Lists are Q-descending, so kets beyond kmax[bra] cannot survive (bound with 4*max_den) and are not visited.
-__global__ void k_enum(const PairEntry* __restrict__ bra, const PairEntry* __restrict__ ket,
-                       const double* __restrict__ Qb, const double* __restrict__ Qk, const double* __restrict__ d4b,
-                       const double* __restrict__ d4k, const int* __restrict__ okb, const int* __restrict__ okk,
-                       const int* __restrict__ canb, const int* __restrict__ cank, const int* __restrict__ kmax,
-                       int p0, int p1, int pstride, int diag, const double* __restrict__ dsh, int nshell, double cutoff,
-                       int2* __restrict__ tasks, unsigned* __restrict__ count, unsigned cap, int use_smem) {
+// Kets at or beyond kmax[bra] cannot survive (suffix maximum of the Schwarz bounds with 4*max_den) and are not
+// visited.  Two passes (count, write) so that the survivors of a bra occupy ONE contiguous segment of the task
+// buffer in ket-list order: a warp of the ERI kernels then sees runs of quartets with the same bra and the same
+// ket shell c.
+constexpr int ENUM_NT = 256;
+__global__ void __launch_bounds__(ENUM_NT)
+k_enum(const PairEntry* __restrict__ bra, const PairEntry* __restrict__ ket, const double* __restrict__ Qb,
+       const double* __restrict__ Qk, const double* __restrict__ d4b, const double* __restrict__ d4k,
+       const int* __restrict__ okb, const int* __restrict__ okk, const int* __restrict__ canb,
+       const int* __restrict__ cank, const int* __restrict__ kmax, int p0, int p1, int pstride, int diag,
+       const double* __restrict__ dsh, int nshell, double cutoff, int2* __restrict__ tasks, unsigned* __restrict__ count,
+       unsigned cap, int use_smem) {
   extern __shared__ double rows[];
+  __shared__ unsigned s_w[ENUM_NT / 32];
+  __shared__ unsigned s_base;
   int p = p0 + blockIdx.x * pstride;
   if (p >= p1) return;
   const PairEntry eb = bra[p];
@@ -331,27 +339,51 @@ __global__ void k_enum(const PairEntry* __restrict__ bra, const PairEntry* __res
   }
   const double qb = Qb[p], db4 = d4b[p];
   const int okp = okb[p], canp = canb[p];
-  for (int q0 = 0; q0 < nk; q0 += blockDim.x) {
-    int q = q0 + threadIdx.x;
-    bool surv = false;
-    if (q < nk) {
-      const PairEntry ek = ket[q];
-      double m = fmax(fmax(fmax(db4, d4k[q]), fmax(rowb[ek.sb], rowb[ek.sa])), fmax(rowa[ek.sb], rowa[ek.sa]));
-      double res = __dmul_rn(__dmul_rn(qb, Qk[q]), m);
-      int bra_ok = (canp >= cank[q]) ? okp : okk[q];  // the canonically larger pair is the reference's bra
-      surv = bra_ok && !(res < cutoff);
+  auto test = [&](int q) {
+    const PairEntry& ek = ket[q];
+    const int sc = ek.sa, sd = ek.sb;
+    double m = fmax(fmax(fmax(db4, d4k[q]), fmax(rowb[sd], rowb[sc])), fmax(rowa[sd], rowa[sc]));
+    double res = __dmul_rn(__dmul_rn(qb, Qk[q]), m);
+    int bra_ok = (canp >= cank[q]) ? okp : okk[q];  // the canonically larger pair is the reference's bra
+    return bra_ok && !(res < cutoff);
+  };
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // pass 1: count
+  unsigned cnt = 0;
+  for (int q = threadIdx.x; q < nk; q += ENUM_NT) cnt += test(q) ? 1u : 0u;
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane == 0) s_w[w] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned tot = 0;
+    for (int k = 0; k < ENUM_NT / 32; ++k) tot += s_w[k];
+    s_base = tot ? atomicAdd(count, tot) : 0u;
+    s_w[0] = tot;  // reused as flag below
+  }
+  __syncthreads();
+  if (s_w[0] == 0) return;
+  unsigned running = s_base;
+  __syncthreads();
+  // pass 2: write in ket-list order
+  for (int q0 = 0; q0 < nk; q0 += ENUM_NT) {
+    const int q = q0 + threadIdx.x;
+    const bool surv = q < nk && test(q);
+    const unsigned mask = __ballot_sync(0xffffffffu, surv);
+    if (lane == 0) s_w[w] = __popc(mask);
+    __syncthreads();
+    unsigned off = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < ENUM_NT / 32; ++k) {
+      const unsigned c = s_w[k];
+      if (k < w) off += c;
+      tot += c;
     }
-    unsigned mask = __ballot_sync(0xffffffffu, surv);
-    if (mask) {
-      int lane = threadIdx.x & 31;
-      unsigned base = 0;
-      if (lane == 0) base = atomicAdd(count, (unsigned)__popc(mask));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (surv) {
-        unsigned pos = base + __popc(mask & ((1u << lane) - 1));
-        if (pos < cap) tasks[pos] = make_int2(p, q);
-      }
+    if (surv) {
+      const unsigned pos = running + off + __popc(mask & ((1u << lane) - 1));
+      if (pos < cap) tasks[pos] = make_int2(p, q);
     }
+    running += tot;
+    __syncthreads();
   }
 }
 
@@ -479,10 +511,30 @@ int build_pairtable(oqpb_ctx* ctx, const Cutoffs& c, PairTable& T, const std::ve
         int j = id - i * (i + 1) / 2;
         return (*Qmat)[(size_t)i * ns + j];
       };
-      std::vector<std::pair<double, int>> key(v.size());
-      for (size_t k = 0; k < v.size(); ++k) key[k] = {-qof(v[k]), v[k]};
-      std::sort(key.begin(), key.end());
-      for (size_t k = 0; k < v.size(); ++k) v[k] = key[k].second;
+      // order: Schwarz bound in descending factor-of-4 bins (keeps the enumeration's early cut-off), inside a bin by
+      // the pair's first (higher angular momentum) shell, so that the surviving kets of a bra come in runs with
+      // the same shell c: the digestion reduces J_ab and the K_ac / K_bc updates of a run inside the warp
+      auto first_shell = [&](int id) {
+        int i = (int)((std::sqrt(8.0 * id + 1.0) - 1.0) * 0.5);
+        while ((long)i * (i + 1) / 2 > id) --i;
+        while ((long)(i + 1) * (i + 2) / 2 <= id) ++i;
+        int j = id - i * (i + 1) / 2;
+        return ctx->am[i] >= ctx->am[j] ? i : j;
+      };
+      struct Key { int bin; int sa; double q; int id; };
+      std::vector<Key> key(v.size());
+      for (size_t k = 0; k < v.size(); ++k) {
+        double q = qof(v[k]);
+        int e = q > 0 ? std::ilogb(q) : -100000;
+        key[k] = {e >= 0 ? e / 2 : -((-e + 1) / 2), first_shell(v[k]), q, v[k]};
+      }
+      std::sort(key.begin(), key.end(), [](const Key& a, const Key& b) {
+        if (a.bin != b.bin) return a.bin > b.bin;
+        if (a.sa != b.sa) return a.sa < b.sa;
+        if (a.q != b.q) return a.q > b.q;
+        return a.id < b.id;
+      });
+      for (size_t k = 0; k < v.size(); ++k) v[k] = key[k].id;
     }
   }
   T.ent.clear(); T.canon.clear(); T.Q.clear();
@@ -511,6 +563,9 @@ int build_pairtable(oqpb_ctx* ctx, const Cutoffs& c, PairTable& T, const std::ve
     }
   }
   T.cls_off[NL] = (int)T.ent.size();
+  T.Qsuf = T.Q;
+  for (int pc = 0; pc < NL; ++pc)
+    for (int k = T.cls_off[pc + 1] - 2; k >= T.cls_off[pc]; --k) T.Qsuf[k] = std::max(T.Qsuf[k], T.Qsuf[k + 1]);
   T.nprim = poff;
   if (poff > 2000000000L) { ctx->err = "pair table too large"; return OQPB_ERR_UNSUPPORTED; }
   int rc;
@@ -656,11 +711,17 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
       const double* Qa = T.Q.data() + T.cls_off[pca];
       const double* Qb = T.Q.data() + T.cls_off[pcb];
       std::vector<int> km(na, 0);
-      int q = nb;  // number of kets that can survive for the current bra (monotone non-increasing in p)
+      // kets at or beyond km[p] cannot survive: suffix maxima of the ket list's bounds are monotone
+      const double* Qs = T.Qsuf.data() + T.cls_off[pcb];
       for (int p = 0; p < na; ++p) {
-        while (q > 0 && ((Qa[p] * Qb[q - 1]) * bound4 < cutoff)) --q;
-        km[p] = q;
+        int lo = 0, hi = nb;  // first k with Qa[p] * Qs[k] * bound4 < cutoff
+        while (lo < hi) {
+          int mid = (lo + hi) / 2;
+          if ((Qa[p] * Qs[mid]) * bound4 < cutoff) hi = mid; else lo = mid + 1;
+        }
+        km[p] = lo;
       }
+      (void)Qb;
       // chunking over this rank's bras (p % nranks == rank)
       size_t cand = 0;
       int p0 = 0;
@@ -733,7 +794,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     int nbra = (ch.p1 - ch.p0 + nr - 1) / nr + 1;
     // first bra of this rank at or after p0
     int pstart = ch.p0 + ((rk - ch.p0 % nr) % nr + nr) % nr;
-    k_enum<<<nbra, 256, use_smem ? smem_rows : 0, cs>>>(
+    k_enum<<<nbra, ENUM_NT, use_smem ? smem_rows : 0, cs>>>(
         T.d_ent.as<PairEntry>() + offa, T.d_ent.as<PairEntry>() + offb, T.d_Q.as<double>() + offa,
         T.d_Q.as<double>() + offb, ctx->d_d4.as<double>() + offa, ctx->d_d4.as<double>() + offb,
         ctx->d_ok.as<int>() + offa, ctx->d_ok.as<int>() + offb, T.d_canon.as<int>() + offa,
