@@ -10,12 +10,12 @@ for out, rx in pairs:
         out, best = out.split("@"); best = int(best)
         cmd = ["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on", "--kernel-name-base", "demangled",
                "-k", f"regex:{rx}", "--launch-skip", str(best), "-c", "1", "-o", f"gpurun_out/{out}", "-f",
-               "python", "tools/scratch/g4.py", wl, "1"]
+               "python", "tools/run_build.py", wl, "1"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         print(out, r.stdout[-200:], flush=True)
         continue
     cmd = ["ncu", "--metrics", "gpu__time_duration.sum", "--clock-control", "none", "--kernel-name-base", "demangled",
-           "-k", f"regex:{rx}", "--csv", "python", "tools/scratch/g4.py", wl, "1"]
+           "-k", f"regex:{rx}", "--csv", "python", "tools/run_build.py", wl, "1"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     rows = [l for l in r.stdout.splitlines() if l.startswith('"')]
     rd = list(csv.DictReader(io.StringIO("\n".join(rows))))
@@ -32,6 +32,6 @@ for out, rx in pairs:
     print(f"{out}: {len(durs)} launches, total {sum(durs)/1e6:.2f} ms, longest #{best} = {durs[best]/1e6:.3f} ms", flush=True)
     cmd = ["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on", "--kernel-name-base", "demangled",
            "-k", f"regex:{rx}", "--launch-skip", str(best), "-c", "1", "-o", f"gpurun_out/{out}", "-f",
-           "python", "tools/scratch/g4.py", wl, "1"]
+           "python", "tools/run_build.py", wl, "1"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     print(r.stdout[-300:])
