@@ -1108,6 +1108,21 @@ constexpr int SMALL_MAX = 36;
 // registers are left to the NCART4 accumulators.
 constexpr int MEDIUM_MAX = 150;
 constexpr int SMALL_NT = 128, MEDIUM_NT = 64;
+// register caps requested from ptxas through __launch_bounds__ (min CTAs/SM = 65536 / (threads * cap)); the kernels are
+// latency bound at 8 warps/SM, so trading a few spills for occupancy pays for some families (tools/tune_variants.sh)
+#ifndef OQPB_SMALL_REGS
+#define OQPB_SMALL_REGS 255
+#endif
+#ifndef OQPB_MED_REGS
+#define OQPB_MED_REGS 255
+#endif
+#ifndef OQPB_GRP_REGS
+#define OQPB_GRP_REGS 255
+#endif
+#ifndef OQPB_REGVRR_MAX
+#define OQPB_REGVRR_MAX 64
+#endif
+__host__ __device__ constexpr int min_ctas(int nt, int regcap) { return regcap >= 255 ? 1 : 65536 / (nt * regcap); }
 
 // Rys evaluation state at X shared by all roots and weights of a primitive quartet
 struct RysX {
@@ -1174,7 +1189,7 @@ __device__ __forceinline__ void rys_pair(const EriArgs& a, const double* __restr
 }
 
 template <int LA, int LB, int LC, int LD, int PV, bool GS>
-__global__ void __launch_bounds__(GS ? MEDIUM_NT : SMALL_NT)
+__global__ void __launch_bounds__(GS ? MEDIUM_NT : SMALL_NT, GS ? min_ctas(MEDIUM_NT, OQPB_MED_REGS) : min_ctas(SMALL_NT, OQPB_SMALL_REGS))
 eri_small_kernel(const EriArgs A) {
   constexpr int NTH = GS ? MEDIUM_NT : SMALL_NT;
   extern __shared__ double gsm[];
@@ -1381,10 +1396,17 @@ struct GroupCfg {
   static constexpr int G = acc_for(4) <= LIMIT ? 4 : (acc_for(8) <= LIMIT ? 8 : (acc_for(16) <= LIMIT ? 16 : 32));
   static constexpr int NVL = (VL + G - 1) / G;
   static constexpr int QPW = 32 / G;
+  // B2 in registers: the 2-D VRR and both HRR transfers of a (root, direction) task run fully unrolled in registers
+  // and only the final [a][b][c][d] table goes to shared memory (the shared-memory pipe is the group kernel's limiter)
+  static constexpr bool REGVRR = C::NMAX * C::MMAX + C::NMAX * C::NKL1 <= OQPB_REGVRR_MAX;
+  static constexpr int GSTR = REGVRR ? (C::G3 | 1) : C::GSTR;   // doubles per (root, direction) table
+  static constexpr int GOFF = REGVRR ? 0 : C::G1 + C::G2;       // offset of the [a][b][c][d] table inside it
+  static constexpr int GREG = 3 * C::R * GSTR;
+  static constexpr int QSM0 = ((GREG > C::BLK ? GREG : C::BLK) + 2 * C::R + 2) | 1;
   // per-quartet stride in doubles: == G (mod 16) for G < 16, so that the 16 lanes of a half-warp (16/G quartets x G
   // lanes, lane stride odd) fall into 16 different 8-byte banks
-  static constexpr int QSMG = G >= 16 ? C::QSM : ((C::QSM + 15 - G) / 16) * 16 + G;
-  static_assert(QSMG >= C::QSM, "QSMG");
+  static constexpr int QSMG = G >= 16 ? QSM0 : ((QSM0 + 15 - G) / 16) * 16 + G;
+  static_assert(QSMG >= QSM0, "QSMG");
   static constexpr int QBYTES = QSMG * 8 + 96 + 128;  // block/g region + QInfo + primitive list
   static constexpr int WPC = (2 * QPW * QBYTES <= 64 * 1024) ? 2 : 1;
   static constexpr int NT = 32 * WPC;
@@ -1392,7 +1414,7 @@ struct GroupCfg {
 };
 
 template <int LA, int LB, int LC, int LD, int PV>
-__global__ void __launch_bounds__(GroupCfg<LA, LB, LC, LD>::NT)
+__global__ void __launch_bounds__(GroupCfg<LA, LB, LC, LD>::NT, min_ctas(GroupCfg<LA, LB, LC, LD>::NT, OQPB_GRP_REGS))
 eri_group_kernel(const EriArgs A) {
   constexpr int N0 = Shell<LA, PV>::NOUT, N1 = Shell<LB, PV>::NOUT, N2 = Shell<LC, PV>::NOUT, N3 = Shell<LD, PV>::NOUT;
   constexpr int NTOT = N0 * N1 * N2 * N3;
@@ -1400,7 +1422,7 @@ eri_group_kernel(const EriArgs A) {
   using GC = GroupCfg<LA, LB, LC, LD>;
   constexpr int R = Cfg::R, NA = Cfg::NA, NB = Cfg::NB, NC = Cfg::NC, ND = Cfg::ND, NKET = Cfg::NKET;
   constexpr int NMAX = Cfg::NMAX, MMAX = Cfg::MMAX, NKL1 = Cfg::NKL1;
-  constexpr int G1 = Cfg::G1, G2 = Cfg::G2, GSTR = Cfg::GSTR, QSM = GC::QSMG;
+  constexpr int G1 = Cfg::G1, G2 = Cfg::G2, GSTR = GC::GSTR, GOFF = GC::GOFF, QSM = GC::QSMG;
   constexpr int G = GC::G, NVL = GC::NVL, QPW = GC::QPW, VL = GC::VL;
   constexpr int LCAP = 64;
   constexpr unsigned FULL = 0xffffffffu;
@@ -1542,6 +1564,45 @@ eri_group_kernel(const EriArgs A) {
             const double b10 = 0.5 * zinv * (1.0 - t2r * zinv);
             const double b01 = 0.5 * einv * (1.0 - t2r * einv);
             const double b00 = 0.5 * t2 * abinv;
+            if constexpr (GC::REGVRR) {
+              double* S3 = qs + (size_t)task * GSTR;
+              double v[NMAX][MMAX];
+              v[0][0] = dir == 0 ? rw[R + r] * pref : 1.0;
+#pragma unroll
+              for (int n = 1; n < NMAX; ++n) v[n][0] = c00 * v[n - 1][0] + (n >= 2 ? (n - 1) * b10 * v[n >= 2 ? n - 2 : 0][0] : 0.0);
+#pragma unroll
+              for (int m = 1; m < MMAX; ++m) {
+                v[0][m] = d00 * v[0][m - 1] + (m >= 2 ? (m - 1) * b01 * v[0][m >= 2 ? m - 2 : 0] : 0.0);
+#pragma unroll
+                for (int n = 1; n < NMAX; ++n)
+                  v[n][m] = d00 * v[n][m - 1] + n * b00 * v[n - 1][m - 1] + (m >= 2 ? (m - 1) * b01 * v[n][m >= 2 ? m - 2 : 0] : 0.0);
+              }
+              double h[NMAX][NKL1];
+#pragma unroll
+              for (int n = 0; n < NMAX; ++n) {
+#pragma unroll
+                for (int c = 0; c <= LC; ++c) h[n][c * (LD + 1)] = v[n][c];
+#pragma unroll
+                for (int d = 1; d <= LD; ++d) {
+#pragma unroll
+                  for (int c = 0; c < MMAX - d; ++c) v[n][c] = v[n][c + 1] + CDd * v[n][c];
+#pragma unroll
+                  for (int c = 0; c <= LC; ++c) h[n][c * (LD + 1) + d] = v[n][c];
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < NKL1; ++k) {
+#pragma unroll
+                for (int a = 0; a <= LA; ++a) S3[(a * (LB + 1)) * NKL1 + k] = h[a][k];
+#pragma unroll
+                for (int b = 1; b <= LB; ++b) {
+#pragma unroll
+                  for (int n = 0; n < NMAX - b; ++n) h[n][k] = h[n + 1][k] + ABd * h[n][k];
+#pragma unroll
+                  for (int a = 0; a <= LA; ++a) S3[(a * (LB + 1) + b) * NKL1 + k] = h[a][k];
+                }
+              }
+            } else {
             double* S1 = qs + (size_t)task * GSTR;
             double* S2 = S1 + G1;
             double* S3 = S2 + G2;
@@ -1573,6 +1634,7 @@ eri_group_kernel(const EriArgs A) {
                 for (int a = 0; a <= LA; ++a) S3[(a * (LB + 1) + b) * NKL1 + k] = S2[a * NKL1 + k];
               }
             }
+            }
           }
         }
         __syncwarp();
@@ -1581,7 +1643,7 @@ eri_group_kernel(const EriArgs A) {
           any = true;
           if (t == 0) ++st_prim;
           for (int r = 0; r < R; ++r) {
-            const double* gbase = qs + (size_t)(3 * r) * GSTR + G1 + G2;
+            const double* gbase = qs + (size_t)(3 * r) * GSTR + GOFF;
 #pragma unroll
             for (int j = 0; j < NVL; ++j) {
               if (t + G * j < VL) {

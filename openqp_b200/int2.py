@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIBPATH = os.path.join(_HERE, "libopenqp_b200.so")
+_LIBPATH = os.environ.get("OQPB_LIB") or os.path.join(_HERE, "libopenqp_b200.so")  # OQPB_LIB: tuning variants (tools/)
 _LIB = None
 
 OQPB_TD_APB, OQPB_TD_AMB, OQPB_TD_TDA, OQPB_TD_TDA_COULOMB = 1, 2, 4, 8
