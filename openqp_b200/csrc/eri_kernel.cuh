@@ -1106,7 +1106,10 @@ constexpr int SMALL_MAX = 36;
 // Medium classes (SMALL_MAX < NCART4 <= MEDIUM_MAX): same one-thread-per-quartet kernel, but the finished
 // gx/gy/gz tables of a root live in shared memory (column per thread, [entry][thread]: conflict-free) so the
 // registers are left to the NCART4 accumulators.
-constexpr int MEDIUM_MAX = 150;
+#ifndef OQPB_MEDIUM_MAX
+#define OQPB_MEDIUM_MAX 150
+#endif
+constexpr int MEDIUM_MAX = OQPB_MEDIUM_MAX;
 constexpr int SMALL_NT = 128, MEDIUM_NT = 64;
 // register caps requested from ptxas through __launch_bounds__ (min CTAs/SM = 65536 / (threads * cap)); the kernels are
 // latency bound at 8 warps/SM, so trading a few spills for occupancy pays for some families (tools/tune_variants.sh)
@@ -1119,10 +1122,20 @@ constexpr int SMALL_NT = 128, MEDIUM_NT = 64;
 #ifndef OQPB_GRP_REGS
 #define OQPB_GRP_REGS 255
 #endif
+#ifndef OQPB_GRP_LIMIT
+#define OQPB_GRP_LIMIT 56
+#endif
 #ifndef OQPB_REGVRR_MAX
 #define OQPB_REGVRR_MAX 64
 #endif
 __host__ __device__ constexpr int min_ctas(int nt, int regcap) { return regcap >= 255 ? 1 : 65536 / (nt * regcap); }
+// measured on (H2O)32/cc-pVTZ: these thread-per-quartet classes gain 4-29 % from a 128-register cap (4 CTAs/SM),
+// the others lose to the spills
+template <int LA, int LB, int LC, int LD>
+__host__ __device__ constexpr int small_regcap() {
+  constexpr int key = LA * 1000 + LB * 100 + LC * 10 + LD;
+  return (key == 2010 || key == 2100 || key == 1100 || key == 1010 || key == 3000) ? 128 : OQPB_SMALL_REGS;
+}
 
 // Rys evaluation state at X shared by all roots and weights of a primitive quartet
 struct RysX {
@@ -1189,7 +1202,7 @@ __device__ __forceinline__ void rys_pair(const EriArgs& a, const double* __restr
 }
 
 template <int LA, int LB, int LC, int LD, int PV, bool GS>
-__global__ void __launch_bounds__(GS ? MEDIUM_NT : SMALL_NT, GS ? min_ctas(MEDIUM_NT, OQPB_MED_REGS) : min_ctas(SMALL_NT, OQPB_SMALL_REGS))
+__global__ void __launch_bounds__(GS ? MEDIUM_NT : SMALL_NT, GS ? min_ctas(MEDIUM_NT, OQPB_MED_REGS) : min_ctas(SMALL_NT, small_regcap<LA, LB, LC, LD>()))
 eri_small_kernel(const EriArgs A) {
   constexpr int NTH = GS ? MEDIUM_NT : SMALL_NT;
   extern __shared__ double gsm[];
@@ -1390,7 +1403,7 @@ struct GroupCfg {
   static constexpr int VL = C::NA * C::NB;
   static constexpr int NKET = C::NKET;
   static constexpr int acc_for(int g) { return ((VL + g - 1) / g) * NKET; }
-  static constexpr int LIMIT = 40;      // accumulators per lane for G < 32
+  static constexpr int LIMIT = OQPB_GRP_LIMIT;  // accumulators per lane for G < 32
   static constexpr int LIMIT32 = 72;    // ... and for full-warp groups
   static constexpr bool OK = (C::KS == 1) && acc_for(32) <= LIMIT32;
   static constexpr int G = acc_for(4) <= LIMIT ? 4 : (acc_for(8) <= LIMIT ? 8 : (acc_for(16) <= LIMIT ? 16 : 32));
