@@ -21,6 +21,38 @@
 #include <type_traits>
 #include <utility>
 
+// ---- tuning knobs (overridable with -D..., see tools/tune_variants.sh)
+#ifndef OQPB_MEDIUM_MAX
+#define OQPB_MEDIUM_MAX 150
+#endif
+#ifndef OQPB_SMALL_REGS
+#define OQPB_SMALL_REGS 255
+#endif
+#ifndef OQPB_MED_REGS
+#define OQPB_MED_REGS 255
+#endif
+#ifndef OQPB_GRP_REGS
+#define OQPB_GRP_REGS 255
+#endif
+#ifndef OQPB_DMMA_MIN_FILL
+#define OQPB_DMMA_MIN_FILL 0.35
+#endif
+#ifndef OQPB_SMALL_GRID
+#define OQPB_SMALL_GRID 8
+#endif
+#ifndef OQPB_DEN_BATCH_MAX
+#define OQPB_DEN_BATCH_MAX 96
+#endif
+#ifndef OQPB_DEN_EARLY_MAX
+#define OQPB_DEN_EARLY_MAX 0
+#endif
+#ifndef OQPB_GRP_LIMIT
+#define OQPB_GRP_LIMIT 56
+#endif
+#ifndef OQPB_REGVRR_MAX
+#define OQPB_REGVRR_MAX 64
+#endif
+
 namespace oqpb {
 
 struct alignas(16) PairEntry {
@@ -289,11 +321,49 @@ __device__ __forceinline__ double seg_sum(double v, const SegMask& m) {
   return v;  // run total in the head lane
 }
 
-// (1) block in registers, one thread: everything unrolled, the density sub-block of a pass is loaded first
+// (1) block in registers, one thread: everything unrolled.  The six density sub-blocks a quartet needs are loaded
+// in ONE batch (DenBlk) so that their L2 latencies overlap; the small classes issue the batch before the primitive loop.
+template <int N0, int N1, int N2, int N3>
+struct DenBlk {
+  static constexpr int SIZE = N2 * N3 + N0 * N1 + N1 * N3 + N1 * N2 + N0 * N3 + N0 * N2;
+  double cd[N2 * N3], ab[N0 * N1], bd[N1 * N3], bc[N1 * N2], ad[N0 * N3], ac[N0 * N2];
+};
+template <int N0, int N1, int N2, int N3>
+__device__ __forceinline__ void den_load(const EriArgs& A, int m, int o0, int o1, int o2, int o3, DenBlk<N0, N1, N2, N3>& D) {
+  const unsigned nbf = (unsigned)A.nbf;
+  const double* __restrict__ DJ = A.DJ[m];
+  const double* __restrict__ DK = A.DK[m];
+#pragma unroll
+  for (int c = 0; c < N2; ++c)
+#pragma unroll
+    for (int d = 0; d < N3; ++d) D.cd[c * N3 + d] = __ldg(DJ + ((unsigned)(o2 + c) * nbf + (unsigned)(o3 + d)));
+#pragma unroll
+  for (int a = 0; a < N0; ++a)
+#pragma unroll
+    for (int b = 0; b < N1; ++b) D.ab[a * N1 + b] = __ldg(DJ + ((unsigned)(o0 + a) * nbf + (unsigned)(o1 + b)));
+#pragma unroll
+  for (int b = 0; b < N1; ++b)
+#pragma unroll
+    for (int d = 0; d < N3; ++d) D.bd[b * N3 + d] = __ldg(DK + ((unsigned)(o1 + b) * nbf + (unsigned)(o3 + d)));
+#pragma unroll
+  for (int b = 0; b < N1; ++b)
+#pragma unroll
+    for (int c = 0; c < N2; ++c) D.bc[b * N2 + c] = __ldg(DK + ((unsigned)(o1 + b) * nbf + (unsigned)(o2 + c)));
+#pragma unroll
+  for (int a = 0; a < N0; ++a)
+#pragma unroll
+    for (int d = 0; d < N3; ++d) D.ad[a * N3 + d] = __ldg(DK + ((unsigned)(o0 + a) * nbf + (unsigned)(o3 + d)));
+#pragma unroll
+  for (int a = 0; a < N0; ++a)
+#pragma unroll
+    for (int c = 0; c < N2; ++c) D.ac[a * N2 + c] = __ldg(DK + ((unsigned)(o0 + a) * nbf + (unsigned)(o2 + c)));
+}
 // All 32 lanes of the warp must call this together (lanes without a quartet pass a zero block).
-template <int N0, int N1, int N2, int N3, bool SEGC>
+// BATCH: all six sub-blocks in registers at once (pre = batch of matrix 0 loaded by the caller when have_pre).
+template <int N0, int N1, int N2, int N3, bool SEGC, bool BATCH>
 __device__ __forceinline__ void digest_sym_reg(const EriArgs& A, const double (&v)[N0 * N1 * N2 * N3], int o0, int o1,
-                                               int o2, int o3, const SegMask& mbra, const SegMask& mc) {
+                                               int o2, int o3, const SegMask& mbra, const SegMask& mc,
+                                               const DenBlk<N0, N1, N2, N3>& pre, bool have_pre) {
   const unsigned nbf = (unsigned)A.nbf;
   const double c4 = 4.0 * A.cj, c1 = A.ck;
 #define VV(a, b, c, d) v[(((a)*N1 + (b)) * N2 + (c)) * N3 + (d)]
@@ -301,12 +371,18 @@ __device__ __forceinline__ void digest_sym_reg(const EriArgs& A, const double (&
     const double* __restrict__ DJ = A.DJ[m];
     const double* __restrict__ DK = A.DK[m];
     double* __restrict__ F = A.F[m];
+    DenBlk<N0, N1, N2, N3> D;
+    if constexpr (BATCH) {
+      if (m == 0 && have_pre) D = pre;
+      else den_load<N0, N1, N2, N3>(A, m, o0, o1, o2, o3, D);
+    }
     {  // J_ab += 4 cj sum_cd v D_cd
-      double dd[N2 * N3];
+      if constexpr (!BATCH) {
 #pragma unroll
-      for (int c = 0; c < N2; ++c)
+        for (int c = 0; c < N2; ++c)
 #pragma unroll
-        for (int d = 0; d < N3; ++d) dd[c * N3 + d] = __ldg(DJ + ((unsigned)(o2 + c) * nbf + (unsigned)(o3 + d)));
+          for (int d = 0; d < N3; ++d) D.cd[c * N3 + d] = __ldg(DJ + ((unsigned)(o2 + c) * nbf + (unsigned)(o3 + d)));
+      }
 #pragma unroll
       for (int a = 0; a < N0; ++a)
 #pragma unroll
@@ -315,17 +391,18 @@ __device__ __forceinline__ void digest_sym_reg(const EriArgs& A, const double (&
 #pragma unroll
           for (int c = 0; c < N2; ++c)
 #pragma unroll
-            for (int d = 0; d < N3; ++d) sum = fma(VV(a, b, c, d), dd[c * N3 + d], sum);
+            for (int d = 0; d < N3; ++d) sum = fma(VV(a, b, c, d), D.cd[c * N3 + d], sum);
           sum = seg_sum(sum, mbra);
           if (mbra.head && sum != 0.0) atomicAdd(F + tri_u(o0 + a, o1 + b), c4 * sum);
         }
     }
     {  // J_cd += 4 cj sum_ab v D_ab
-      double dd[N0 * N1];
+      if constexpr (!BATCH) {
 #pragma unroll
-      for (int a = 0; a < N0; ++a)
+        for (int a = 0; a < N0; ++a)
 #pragma unroll
-        for (int b = 0; b < N1; ++b) dd[a * N1 + b] = __ldg(DJ + ((unsigned)(o0 + a) * nbf + (unsigned)(o1 + b)));
+          for (int b = 0; b < N1; ++b) D.ab[a * N1 + b] = __ldg(DJ + ((unsigned)(o0 + a) * nbf + (unsigned)(o1 + b)));
+      }
 #pragma unroll
       for (int c = 0; c < N2; ++c)
 #pragma unroll
@@ -334,16 +411,17 @@ __device__ __forceinline__ void digest_sym_reg(const EriArgs& A, const double (&
 #pragma unroll
           for (int a = 0; a < N0; ++a)
 #pragma unroll
-            for (int b = 0; b < N1; ++b) sum = fma(VV(a, b, c, d), dd[a * N1 + b], sum);
+            for (int b = 0; b < N1; ++b) sum = fma(VV(a, b, c, d), D.ab[a * N1 + b], sum);
           if (sum != 0.0) atomicAdd(F + tri_u(o2 + c, o3 + d), c4 * sum);
         }
     }
     {  // K_ac -= ck sum_bd v D_bd
-      double dd[N1 * N3];
+      if constexpr (!BATCH) {
 #pragma unroll
-      for (int b = 0; b < N1; ++b)
+        for (int b = 0; b < N1; ++b)
 #pragma unroll
-        for (int d = 0; d < N3; ++d) dd[b * N3 + d] = __ldg(DK + ((unsigned)(o1 + b) * nbf + (unsigned)(o3 + d)));
+          for (int d = 0; d < N3; ++d) D.bd[b * N3 + d] = __ldg(DK + ((unsigned)(o1 + b) * nbf + (unsigned)(o3 + d)));
+      }
 #pragma unroll
       for (int a = 0; a < N0; ++a)
 #pragma unroll
@@ -352,17 +430,18 @@ __device__ __forceinline__ void digest_sym_reg(const EriArgs& A, const double (&
 #pragma unroll
           for (int b = 0; b < N1; ++b)
 #pragma unroll
-            for (int d = 0; d < N3; ++d) sum = fma(VV(a, b, c, d), dd[b * N3 + d], sum);
+            for (int d = 0; d < N3; ++d) sum = fma(VV(a, b, c, d), D.bd[b * N3 + d], sum);
           if constexpr (SEGC) sum = seg_sum(sum, mc);
           if ((!SEGC || mc.head) && sum != 0.0) atomicAdd(F + tri_u(o0 + a, o2 + c), -c1 * sum);
         }
     }
     {  // K_ad -= ck sum_bc v D_bc
-      double dd[N1 * N2];
+      if constexpr (!BATCH) {
 #pragma unroll
-      for (int b = 0; b < N1; ++b)
+        for (int b = 0; b < N1; ++b)
 #pragma unroll
-        for (int c = 0; c < N2; ++c) dd[b * N2 + c] = __ldg(DK + ((unsigned)(o1 + b) * nbf + (unsigned)(o2 + c)));
+          for (int c = 0; c < N2; ++c) D.bc[b * N2 + c] = __ldg(DK + ((unsigned)(o1 + b) * nbf + (unsigned)(o2 + c)));
+      }
 #pragma unroll
       for (int a = 0; a < N0; ++a)
 #pragma unroll
@@ -371,16 +450,17 @@ __device__ __forceinline__ void digest_sym_reg(const EriArgs& A, const double (&
 #pragma unroll
           for (int b = 0; b < N1; ++b)
 #pragma unroll
-            for (int c = 0; c < N2; ++c) sum = fma(VV(a, b, c, d), dd[b * N2 + c], sum);
+            for (int c = 0; c < N2; ++c) sum = fma(VV(a, b, c, d), D.bc[b * N2 + c], sum);
           if (sum != 0.0) atomicAdd(F + tri_u(o0 + a, o3 + d), -c1 * sum);
         }
     }
     {  // K_bc -= ck sum_ad v D_ad
-      double dd[N0 * N3];
+      if constexpr (!BATCH) {
 #pragma unroll
-      for (int a = 0; a < N0; ++a)
+        for (int a = 0; a < N0; ++a)
 #pragma unroll
-        for (int d = 0; d < N3; ++d) dd[a * N3 + d] = __ldg(DK + ((unsigned)(o0 + a) * nbf + (unsigned)(o3 + d)));
+          for (int d = 0; d < N3; ++d) D.ad[a * N3 + d] = __ldg(DK + ((unsigned)(o0 + a) * nbf + (unsigned)(o3 + d)));
+      }
 #pragma unroll
       for (int b = 0; b < N1; ++b)
 #pragma unroll
@@ -389,17 +469,18 @@ __device__ __forceinline__ void digest_sym_reg(const EriArgs& A, const double (&
 #pragma unroll
           for (int a = 0; a < N0; ++a)
 #pragma unroll
-            for (int d = 0; d < N3; ++d) sum = fma(VV(a, b, c, d), dd[a * N3 + d], sum);
+            for (int d = 0; d < N3; ++d) sum = fma(VV(a, b, c, d), D.ad[a * N3 + d], sum);
           if constexpr (SEGC) sum = seg_sum(sum, mc);
           if ((!SEGC || mc.head) && sum != 0.0) atomicAdd(F + tri_u(o1 + b, o2 + c), -c1 * sum);
         }
     }
     {  // K_bd -= ck sum_ac v D_ac
-      double dd[N0 * N2];
+      if constexpr (!BATCH) {
 #pragma unroll
-      for (int a = 0; a < N0; ++a)
+        for (int a = 0; a < N0; ++a)
 #pragma unroll
-        for (int c = 0; c < N2; ++c) dd[a * N2 + c] = __ldg(DK + ((unsigned)(o0 + a) * nbf + (unsigned)(o2 + c)));
+          for (int c = 0; c < N2; ++c) D.ac[a * N2 + c] = __ldg(DK + ((unsigned)(o0 + a) * nbf + (unsigned)(o2 + c)));
+      }
 #pragma unroll
       for (int b = 0; b < N1; ++b)
 #pragma unroll
@@ -408,7 +489,7 @@ __device__ __forceinline__ void digest_sym_reg(const EriArgs& A, const double (&
 #pragma unroll
           for (int a = 0; a < N0; ++a)
 #pragma unroll
-            for (int c = 0; c < N2; ++c) sum = fma(VV(a, b, c, d), dd[a * N2 + c], sum);
+            for (int c = 0; c < N2; ++c) sum = fma(VV(a, b, c, d), D.ac[a * N2 + c], sum);
           if (sum != 0.0) atomicAdd(F + tri_u(o1 + b, o3 + d), -c1 * sum);
         }
     }
@@ -768,6 +849,145 @@ __device__ __forceinline__ void digest_gen(const EriArgs& A, const double* blk, 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// MODE_GEN, warp-cooperative: one finished block in shared memory is digested by all 32 lanes for ALL matrices.
+// A contraction  out(m, o) = sum_k P_m(k) V(k, o)  (o = output AO pair, k = contracted AO pair, m = matrix) is a small
+// dense GEMM with M = number of matrices (nvec x 7 for MRSF, tdhf_mrsf_lib.F90:279-310): it runs on the FP64 tensor
+// cores (DMMA m8n8k4; A = density rows, contiguous in m; B = block elements from shared memory) when the (o, k) tile
+// is reasonably full, otherwise as a scalar loop with lanes over (o, m), m fastest (coalesced P reads and reds).
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+// X < Y: positions (0..3 = a,b,c,d) of the output pair; the other two positions (U < V) are contracted.
+template <int N0, int N1, int N2, int N3, int X, int Y>
+__device__ __forceinline__ void gen_contract(const EriArgs& A, const double* __restrict__ blk, const int (&off)[4], int lane) {
+  constexpr int N[4] = {N0, N1, N2, N3};
+  constexpr int STR[4] = {N1 * N2 * N3, N2 * N3, N3, 1};
+  constexpr bool COUL = (X == 0 && Y == 1) || (X == 2 && Y == 3);
+  constexpr int U = (X != 0 && Y != 0) ? 0 : ((X != 1 && Y != 1) ? 1 : 2);
+  constexpr int V = (X != 3 && Y != 3) ? 3 : ((X != 2 && Y != 2) ? 2 : 1);
+  static_assert(U < V && U != X && U != Y && V != X && V != Y, "gen_contract: index positions");
+  constexpr int NO = N[X] * N[Y], NK = N[U] * N[V];
+  constexpr int KT = (NK + 3) / 4, OT = (NO + 7) / 8;
+  constexpr bool USE_MMA = (double)(NO * NK) / (double)(OT * 8 * KT * 4) >= OQPB_DMMA_MIN_FILL;
+  const int NM = A.gen_nmat_total;
+  const int mrows = COUL ? A.gen_ncoul * A.gen_nvec : NM;
+  const double scale = COUL ? A.cj : -A.ck;
+  if (mrows <= 0 || scale == 0.0) return;
+  const size_t nbf = (size_t)A.nbf;
+  const double* __restrict__ P = A.Pgen;
+  double* __restrict__ F = A.Fgen;
+  if constexpr (USE_MMA) {
+    const int kl = lane & 3, rl = lane >> 2;
+    size_t pa1[KT], pa2[KT];
+    int vofs[KT];
+    bool kok[KT];
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      const int k = kt * 4 + kl;
+      kok[kt] = k < NK;
+      const int kk = kok[kt] ? k : 0;
+      const int iu = kk / N[V], iv = kk % N[V];
+      const size_t p = (size_t)(off[U] + iu), q = (size_t)(off[V] + iv);
+      pa1[kt] = (q * nbf + p) * NM;
+      pa2[kt] = (p * nbf + q) * NM;
+      vofs[kt] = iu * STR[U] + iv * STR[V];
+    }
+    const int MT = (mrows + 7) >> 3;
+#pragma unroll 1
+    for (int ot = 0; ot < OT; ++ot) {
+      const int o = ot * 8 + rl;
+      const bool ook = o < NO;
+      const int oo = ook ? o : 0;
+      const int obase = (oo / N[Y]) * STR[X] + (oo % N[Y]) * STR[Y];
+      double bf[KT];
+#pragma unroll
+      for (int kt = 0; kt < KT; ++kt) bf[kt] = (ook && kok[kt]) ? blk[obase + vofs[kt]] : 0.0;
+      size_t f1[2], f2[2];
+      bool fok[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int oc = ot * 8 + 2 * kl + j;
+        fok[j] = oc < NO;
+        const int occ = fok[j] ? oc : 0;
+        const size_t p = (size_t)(off[X] + occ / N[Y]), q = (size_t)(off[Y] + occ % N[Y]);
+        f1[j] = (q * nbf + p) * NM;
+        f2[j] = (p * nbf + q) * NM;
+      }
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const int m = mt * 8 + rl;
+        const bool mok = m < mrows;
+        double c10 = 0.0, c11 = 0.0, c20 = 0.0, c21 = 0.0;
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) {
+          const bool ld = mok && kok[kt];
+          double a1 = ld ? __ldg(P + pa1[kt] + m) : 0.0;
+          const double a2 = ld ? __ldg(P + pa2[kt] + m) : 0.0;
+          if constexpr (COUL) {
+            a1 += a2;
+            dmma_m8n8k4(c10, c11, a1, bf[kt]);
+          } else {
+            dmma_m8n8k4(c10, c11, a1, bf[kt]);
+            dmma_m8n8k4(c20, c21, a2, bf[kt]);
+          }
+        }
+        if (mok) {
+          if constexpr (COUL) {
+            if (fok[0] && c10 != 0.0) { atomicAdd(F + f1[0] + m, scale * c10); atomicAdd(F + f2[0] + m, scale * c10); }
+            if (fok[1] && c11 != 0.0) { atomicAdd(F + f1[1] + m, scale * c11); atomicAdd(F + f2[1] + m, scale * c11); }
+          } else {
+            if (fok[0]) {
+              if (c10 != 0.0) atomicAdd(F + f1[0] + m, scale * c10);
+              if (c20 != 0.0) atomicAdd(F + f2[0] + m, scale * c20);
+            }
+            if (fok[1]) {
+              if (c11 != 0.0) atomicAdd(F + f1[1] + m, scale * c11);
+              if (c21 != 0.0) atomicAdd(F + f2[1] + m, scale * c21);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    for (int e = lane; e < NO * mrows; e += 32) {
+      const int m = e % mrows, o = e / mrows;
+      const int ix = o / N[Y], iy = o % N[Y];
+      const double* v = blk + ix * STR[X] + iy * STR[Y];
+      double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int iu = 0; iu < N[U]; ++iu)
+#pragma unroll
+        for (int iv = 0; iv < N[V]; ++iv) {
+          const size_t p = (size_t)(off[U] + iu), q = (size_t)(off[V] + iv);
+          const double x = v[iu * STR[U] + iv * STR[V]];
+          s1 = fma(x, __ldg(P + (q * nbf + p) * NM + m), s1);
+          s2 = fma(x, __ldg(P + (p * nbf + q) * NM + m), s2);
+        }
+      const size_t p = (size_t)(off[X] + ix), q = (size_t)(off[Y] + iy);
+      if constexpr (COUL) {
+        const double sj = s1 + s2;
+        if (sj != 0.0) { atomicAdd(F + (q * nbf + p) * NM + m, scale * sj); atomicAdd(F + (p * nbf + q) * NM + m, scale * sj); }
+      } else {
+        if (s1 != 0.0) atomicAdd(F + (q * nbf + p) * NM + m, scale * s1);
+        if (s2 != 0.0) atomicAdd(F + (p * nbf + q) * NM + m, scale * s2);
+      }
+    }
+  }
+}
+// all 32 lanes together; blk[a][b][c][d] in shared memory (element cutoff and coincidence factor applied)
+template <int N0, int N1, int N2, int N3>
+__device__ __forceinline__ void digest_gen_warp(const EriArgs& A, const double* blk, const int (&off)[4], int lane) {
+  gen_contract<N0, N1, N2, N3, 0, 1>(A, blk, off, lane);  // Coulomb on (a,b),(b,a)
+  gen_contract<N0, N1, N2, N3, 2, 3>(A, blk, off, lane);  // Coulomb on (c,d),(d,c)
+  gen_contract<N0, N1, N2, N3, 0, 2>(A, blk, off, lane);  // exchange (a,c),(c,a)
+  gen_contract<N0, N1, N2, N3, 0, 3>(A, blk, off, lane);
+  gen_contract<N0, N1, N2, N3, 1, 2>(A, blk, off, lane);
+  gen_contract<N0, N1, N2, N3, 1, 3>(A, blk, off, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------
 template <int LA, int LB, int LC, int LD, int PV>
 __global__ void __launch_bounds__(ClassCfg<LA, LB, LC, LD>::NT)
 eri_kernel(const EriArgs A) {
@@ -1106,28 +1326,10 @@ constexpr int SMALL_MAX = 36;
 // Medium classes (SMALL_MAX < NCART4 <= MEDIUM_MAX): same one-thread-per-quartet kernel, but the finished
 // gx/gy/gz tables of a root live in shared memory (column per thread, [entry][thread]: conflict-free) so the
 // registers are left to the NCART4 accumulators.
-#ifndef OQPB_MEDIUM_MAX
-#define OQPB_MEDIUM_MAX 150
-#endif
 constexpr int MEDIUM_MAX = OQPB_MEDIUM_MAX;
 constexpr int SMALL_NT = 128, MEDIUM_NT = 64;
 // register caps requested from ptxas through __launch_bounds__ (min CTAs/SM = 65536 / (threads * cap)); the kernels are
 // latency bound at 8 warps/SM, so trading a few spills for occupancy pays for some families (tools/tune_variants.sh)
-#ifndef OQPB_SMALL_REGS
-#define OQPB_SMALL_REGS 255
-#endif
-#ifndef OQPB_MED_REGS
-#define OQPB_MED_REGS 255
-#endif
-#ifndef OQPB_GRP_REGS
-#define OQPB_GRP_REGS 255
-#endif
-#ifndef OQPB_GRP_LIMIT
-#define OQPB_GRP_LIMIT 56
-#endif
-#ifndef OQPB_REGVRR_MAX
-#define OQPB_REGVRR_MAX 64
-#endif
 __host__ __device__ constexpr int min_ctas(int nt, int regcap) { return regcap >= 255 ? 1 : 65536 / (nt * regcap); }
 // measured on (H2O)32/cc-pVTZ: these thread-per-quartet classes gain 4-29 % from a 128-register cap (4 CTAs/SM),
 // the others lose to the spills
@@ -1227,6 +1429,18 @@ eri_small_kernel(const EriArgs A) {
     const int2 tk = A.tasks[valid ? ti : ntasks - 1];
     PairEntry pb = A.bra[tk.x], pk = A.ket[tk.y];
     if (!valid) pb.pcnt = pk.pcnt = 0;  // no primitive work, zero block
+    // task of this lane's NEXT iteration: its pair entries are pulled towards the SM while this quartet is computed
+    const unsigned tnext = ti + gridDim.x * blockDim.x;
+    int2 tkn = make_int2(-1, -1);
+    if (tnext < ntasks) tkn = A.tasks[tnext];
+    // density sub-blocks of matrix 0: issued now, consumed by the digestion after the primitive loop
+    using Den = DenBlk<N0, N1, N2, N3>;
+    constexpr bool DEN_BATCH = Den::SIZE + NTOT <= OQPB_DEN_BATCH_MAX;
+    constexpr bool DEN_EARLY = DEN_BATCH && Den::SIZE <= OQPB_DEN_EARLY_MAX;
+    Den den0;
+    if constexpr (DEN_EARLY) {
+      if (A.mode == MODE_SYM) den_load<N0, N1, N2, N3>(A, 0, pb.oa, pb.ob, pk.oa, pk.ob, den0);
+    }
     const double Ax = pb.ax, Ay = pb.ay, Az = pb.az, Cx = pk.ax, Cy = pk.ay, Cz = pk.az;
     const double AB[3] = {pb.abx, pb.aby, pb.abz};
     const double CD[3] = {pk.abx, pk.aby, pk.abz};
@@ -1331,7 +1545,15 @@ eri_small_kernel(const EriArgs A) {
         }
       }
     }
-    if (A.mode != MODE_SYM && !any) {  // (mode is uniform; MODE_SYM keeps the warp together for the reductions)
+    if (tkn.x >= 0) {
+      const char* nb_ = reinterpret_cast<const char*>(A.bra + tkn.x);
+      const char* nk_ = reinterpret_cast<const char*>(A.ket + tkn.y);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(nb_));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(nb_ + 64));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(nk_));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(nk_ + 64));
+    }
+    if (A.mode != MODE_SYM && A.mode != MODE_GEN && !any) {  // (mode is uniform; SYM / GEN keep the warp together)
       if (valid && A.mode == MODE_SCHWARZ) A.qout[tk.x] = 0.0;
       if (valid && A.mode == MODE_BLOCK)
         for (int e = 0; e < NTOT; ++e) A.blockout[e] = 0.0;
@@ -1377,12 +1599,24 @@ eri_small_kernel(const EriArgs A) {
       const long long kbra = valid ? (long long)tk.x : -1 - (long long)lane;
       const SegMask mbra = seg_make(kbra, lane);
       const SegMask mc = seg_make(valid ? ((long long)tk.x << 20) | (long long)pk.sa : kbra, lane);
-      digest_sym_reg<N0, N1, N2, N3, !GS>(A, blk, pb.oa, pb.ob, pk.oa, pk.ob, mbra, mc);
-    } else if (valid) {
-      double loc[NTOT];
+      digest_sym_reg<N0, N1, N2, N3, !GS, DEN_BATCH>(A, blk, pb.oa, pb.ob, pk.oa, pk.ob, mbra, mc, den0, DEN_EARLY);
+    } else {
+      // MODE_GEN: the 32 blocks of the warp go to shared memory and are digested one after the other by all lanes
+      constexpr int GBS = NTOT | 1;
+      double* wb = gsm + (GS ? 3 * NIJ1 * NKL1 * NTH : (RSM ? RysSmem<R>::doubles(A.rys_xmax) : 0)) +
+                   (size_t)(threadIdx.x >> 5) * (32 * GBS);
+      __syncwarp();
 #pragma unroll
-      for (int e = 0; e < NTOT; ++e) loc[e] = blk[e];
-      digest_gen<N0, N1, N2, N3>(A, loc, pb.oa, pb.ob, pk.oa, pk.ob, 0, 1);
+      for (int e = 0; e < NTOT; ++e) wb[lane * GBS + e] = blk[e];
+      __syncwarp();
+      unsigned live = __ballot_sync(0xffffffffu, valid && any);
+      while (live) {
+        const int q = __ffs(live) - 1;
+        live &= live - 1;
+        const int off[4] = {__shfl_sync(0xffffffffu, pb.oa, q), __shfl_sync(0xffffffffu, pb.ob, q),
+                            __shfl_sync(0xffffffffu, pk.oa, q), __shfl_sync(0xffffffffu, pk.ob, q)};
+        digest_gen_warp<N0, N1, N2, N3>(A, wb + q * GBS, off, lane);
+      }
     }
   }
   if (A.stat) {
@@ -1754,8 +1988,16 @@ eri_group_kernel(const EriArgs A) {
       const GroupSeg<G> mbra = gseg_make<G>(kbra, lane);
       const GroupSeg<G> mc = gseg_make<G>(valid ? ((long long)qi.bra_id << 20) | (long long)qi.sc : kbra, lane);
       digest_sym_group<N0, N1, N2, N3, G>(A, src, qi.oa, qi.ob, qi.oc, qi.od, t, work, mbra, mc);
-    } else if (work) {
-      digest_gen<N0, N1, N2, N3>(A, src, qi.oa, qi.ob, qi.oc, qi.od, t, G);
+    } else {
+      // MODE_GEN: the quartets of the warp one after the other, each digested by all 32 lanes (DMMA)
+      const int srcoff = (int)(src - qs);
+#pragma unroll 1
+      for (int gq = 0; gq < QPW; ++gq) {
+        if (!__shfl_sync(FULL, work ? 1 : 0, gq * G)) continue;
+        const QInfo& qq = *reinterpret_cast<const QInfo*>(tail + (size_t)(w * QPW + gq) * 96);
+        const int off[4] = {qq.oa, qq.ob, qq.oc, qq.od};
+        digest_gen_warp<N0, N1, N2, N3>(A, smem + (size_t)(w * QPW + gq) * QSM + srcoff, off, lane);
+      }
     }
   }
   if (A.stat) {
@@ -1769,15 +2011,28 @@ cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
   using Cfg = ClassCfg<LA, LB, LC, LD>;
   if constexpr (Cfg::NCART4 <= SMALL_MAX) {
     constexpr int R = Cfg::R;
-    const size_t smem = RysSmem<R>::USE ? (size_t)RysSmem<R>::doubles(args.rys_xmax) * sizeof(double) : 0;
+    constexpr int NTOT = Shell<LA, PV>::NOUT * Shell<LB, PV>::NOUT * Shell<LC, PV>::NOUT * Shell<LD, PV>::NOUT;
+    constexpr size_t gen = (size_t)(SMALL_NT / 32) * 32 * (NTOT | 1) * sizeof(double);  // MODE_GEN block staging
+    const size_t smem = (RysSmem<R>::USE ? (size_t)RysSmem<R>::doubles(args.rys_xmax) * sizeof(double) : 0) +
+                        (args.mode == MODE_GEN ? gen : 0);
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(eri_small_kernel<LA, LB, LC, LD, PV, false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
     eri_small_kernel<LA, LB, LC, LD, PV, false><<<nblocks, SMALL_NT, smem, st>>>(args);
     return cudaGetLastError();
   } else if constexpr (Cfg::NCART4 <= MEDIUM_MAX) {
-    constexpr size_t smem = (size_t)3 * Cfg::NIJ1 * Cfg::NKL1 * MEDIUM_NT * sizeof(double);
+    constexpr int NTOT = Shell<LA, PV>::NOUT * Shell<LB, PV>::NOUT * Shell<LC, PV>::NOUT * Shell<LD, PV>::NOUT;
+    constexpr size_t gen = (size_t)(MEDIUM_NT / 32) * 32 * (NTOT | 1) * sizeof(double);  // MODE_GEN block staging
+    constexpr size_t smem0 = (size_t)3 * Cfg::NIJ1 * Cfg::NKL1 * MEDIUM_NT * sizeof(double);
+    const size_t smem = smem0 + (args.mode == MODE_GEN ? gen : 0);
     static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
+    if (!attr_set && smem0 + gen > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(eri_small_kernel<LA, LB, LC, LD, PV, true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem0 + gen));
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
@@ -1814,8 +2069,15 @@ constexpr int class_tasks_per_cta() {
   return C::NCART4 <= SMALL_MAX ? SMALL_NT : (C::NCART4 <= MEDIUM_MAX ? MEDIUM_NT : (GC::OK ? GC::WPC * GC::QPW : C::QPB));
 }
 
+// grid cap: the thread-per-quartet kernels with a Rys table prologue run about two waves of resident CTAs
+template <int LA, int LB, int LC, int LD>
+constexpr int class_max_ctas() {
+  using C = ClassCfg<LA, LB, LC, LD>;
+  return (C::NCART4 <= SMALL_MAX && RysSmem<C::R>::USE) ? 148 * OQPB_SMALL_GRID : 148 * 32;
+}
+
 using LaunchFn = cudaError_t (*)(const EriArgs&, int, cudaStream_t);
-struct ClassEntry { LaunchFn launch; int qpb; int nt; size_t smem; };
+struct ClassEntry { LaunchFn launch; int qpb; int nt; size_t smem; int maxcta; };
 // class table: [pure variant PV = (d pure) | (f pure) << 1][quartet class]
 const ClassEntry* class_table(int pv);
 

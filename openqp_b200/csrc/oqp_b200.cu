@@ -816,7 +816,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     A.Pgen = S.Pgen; A.Fgen = S.Fgen; A.gen_nmat_total = S.gen_nm; A.gen_ncoul = S.gen_ncoul; A.gen_nvec = S.gen_nvec;
     const int qcls = quartet_class(pc_of(ch.pca), pc_of(ch.pcb));
     const ClassEntry& ce = tab[qcls];
-    size_t nb = std::min<size_t>((ch.cand + ce.qpb - 1) / ce.qpb, (size_t)148 * 32);
+    size_t nb = std::min<size_t>((ch.cand + ce.qpb - 1) / ce.qpb, (size_t)ce.maxcta);
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (ctx->profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, cs); }
     CK(ce.launch(A, (int)std::max<size_t>(nb, 1), cs));

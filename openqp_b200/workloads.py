@@ -40,3 +40,15 @@ def scale_exchange(name: str) -> float:
 def build(name: str):
     mol, bs = B.build(name)
     return mol, bs
+
+
+def mrsf_densities(bs, nvec: int, ncomp: int = 7, seed: int = 7, decay: float = 0.6) -> np.ndarray:
+    """d3(nvec, 7, nbf, nbf): general (non-symmetric) trial densities of the shape `mrsfcbc` produces
+    (tdhf_mrsf_lib.F90:940-1010), here random with the same distance decay as `synthetic_density`."""
+    rng = np.random.default_rng(seed)
+    cen = np.repeat(bs.centers, bs.naos, axis=0)
+    g = cen @ cen.T
+    sq = np.diag(g)
+    r = np.sqrt(np.maximum(sq[:, None] + sq[None, :] - 2 * g, 0.0))
+    env = np.exp(-decay * r)
+    return rng.normal(size=(nvec, ncomp, bs.nbf, bs.nbf)) * env[None, None] * 0.1

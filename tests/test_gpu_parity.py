@@ -207,6 +207,19 @@ def test_mrsf_consumer(oracle_mod, drv):
     assert c.skipped == st["nschwz"]
 
 
+def test_mrsf_consumer_dmma_pure_d(oracle_mod, drv):
+    """Batched multi-density digestion on the FP64 tensor cores (DMMA m8n8k4, eri_kernel.cuh gen_contract): pure 5d
+    shells, a matrix count (5 x 7 = 35) that is not a multiple of the 8-row MMA tile, Coulomb on 20 of the 35."""
+    from openqp_b200.int2 import Int2MrsfData
+    bs, o = _pair(oracle_mod, drv, B.water(), "cc-pvdz", cutoff=1e-9)
+    rng = np.random.default_rng(11)
+    d3 = rng.normal(size=(5, 7, bs.nbf, bs.nbf)) * 0.1
+    c = drv.run(Int2MrsfData(d3, scale_exchange=0.7, scale_coulomb=0.9))
+    f3, st = o.mrsf(d3, 0.7, 0.9)
+    assert np.abs(c.f3 - f3).max() < 1e-10
+    assert c.skipped == st["nschwz"]
+
+
 def test_legacy_seam_routec_fock_jk(oracle_mod, drv):
     """routec_fock_jk (routec_bridge.F90:33-40): by-reference scalars, f returned ready to use, info = 0."""
     from openqp_b200.int2 import lib
