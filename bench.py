@@ -32,6 +32,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nvec", type=int, default=12, help="MRSF workloads (c5): Davidson trial vectors per build (x 7 densities)")
     return ap.parse_args()
 
 
@@ -112,6 +113,166 @@ def cpu_sample(bs, d_packed, sx, target_s, nthreads=0):
     return {"quartets": st["nquartets"], "seconds": dt, "stride": stride, "cores": max_threads() if nthreads == 0 else nthreads}
 
 
+MRSF_WORKLOADS = ("c5",)
+
+
+def mrsf_cpu_sample(bs, d3, sx, target_s, nthreads=0):
+    """Oracle int2_mrsf_data_t build (tdhf_mrsf_lib.F90:218-333) on a strided sample of the bra shell-pair list."""
+    from oracle.oracle import Oracle, max_threads
+    o = Oracle(bs)
+    o.set_screening()
+    npair = bs.nshell * (bs.nshell + 1) // 2
+    stride = max(1, npair // 200)
+    t = time.perf_counter()
+    _, st = o.mrsf(d3, sx, 1.0, nthreads=nthreads, stride=stride, offset=1 % stride)
+    dt = time.perf_counter() - t
+    stride2 = max(1, int(round(dt * stride / target_s)))
+    if stride2 < stride:
+        t = time.perf_counter()
+        _, st = o.mrsf(d3, sx, 1.0, nthreads=nthreads, stride=stride2, offset=1 % stride2)
+        dt = time.perf_counter() - t
+        stride = stride2
+    return {"quartets": st["nquartets"], "seconds": dt, "stride": stride, "cores": max_threads() if nthreads == 0 else nthreads}
+
+
+def main_mrsf(args):
+    """config 5: one step = one int2_mrsf_data_t build, nvec x 7 general densities digested in one pass over the
+    surviving quartets (batched multi-density J/K for the MRSF Davidson trial vectors)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from openqp_b200 import workloads as W
+    from openqp_b200.int2 import Int2Compute, lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    mol, bs = W.build(args.workload)
+    nvec, ncomp, sx = args.nvec, 7, 0.5  # BHHLYP: 50 % exact exchange
+    d3 = W.mrsf_densities(bs, nvec, ncomp)
+    d3f = np.ascontiguousarray(np.transpose(d3, (3, 2, 1, 0)))  # Fortran d3(v, c, mu, nu), v fastest
+    drv = Int2Compute(local).init(bs)
+    t0 = time.perf_counter()
+    drv.set_screening()
+    t_screen = time.perf_counter() - t0
+    drv.set_partition(rank, world)
+    stream = torch.cuda.current_stream(dev)
+    drv.set_stream(stream.cuda_stream)
+    fp64_peak = drv.fp64_peak_tflops()
+    d_dev = torch.from_numpy(d3f).to(dev)
+    f_dev = torch.zeros_like(d_dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def step_dev():
+        drv.mrsf_dev(d_dev.data_ptr(), f_dev.data_ptr(), nvec, ncomp, scale_exchange=sx, scale_coulomb=1.0)
+        if world > 1:
+            dist.all_reduce(f_dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot_ms, kernel_ms, flops, nq, launches = 0.0, 0.0, 0.0, 0, 0
+    for _ in range(args.steps):
+        flush.fill_(1.0)
+        barrier()
+        ev0.record(stream)
+        step_dev()
+        ev1.record(stream)
+        barrier()
+        tot_ms += ev0.elapsed_time(ev1)
+        st = drv.last_stats()
+        kernel_ms += st["kernel_ms"]; flops += st["flops"]; nq += st["nquartets"]; launches += st["launches"] + 3
+    t = torch.tensor([tot_ms, float(nq), flops, kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        tot_ms, kernel_ms = float(tmax[0]), float(tmax[3])
+        nq_all, flops_all = float(tsum[1]), float(tsum[2])
+    else:
+        nq_all, flops_all = float(nq), flops
+    clocks = sampler.stop() if rank == 0 else None
+
+    # e2e: the reference-facing call with HOST buffers (pinned): H2D of d3, build, D2H of f3 inside the timed region
+    d_pin = torch.from_numpy(d3f).pin_memory()
+    f_pin = torch.empty_like(d_pin)
+    ns = C.c_longlong(0)
+
+    def step_host():
+        if world == 1:
+            rc = lib().oqpb_jk_mrsf(drv._h, C.c_void_p(d_pin.data_ptr()), nvec, ncomp, C.c_double(sx), C.c_double(1.0),
+                                    C.c_void_p(f_pin.data_ptr()), C.byref(ns))
+            assert rc == 0
+        else:
+            d_dev.copy_(d_pin, non_blocking=True)
+            step_dev()
+            f_pin.copy_(f_dev, non_blocking=True)
+            torch.cuda.synchronize(dev)
+
+    step_host()
+    barrier()
+    e2e_ms = 0.0
+    for _ in range(args.steps):
+        flush.fill_(1.0)
+        barrier()
+        ev0.record(stream)
+        step_host()
+        ev1.record(stream)
+        barrier()
+        e2e_ms += ev0.elapsed_time(ev1)
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te[0])
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        ms_per_step = tot_ms / args.steps
+        nq_step = nq_all / args.steps
+        achieved = flops_all / world / (kernel_ms * 1e-3) / 1e12 if kernel_ms > 0 else 0.0
+        nbytes = d3f.nbytes
+        line = {
+            "metric": "shell_quartets_per_s", "value": nq_step / (ms_per_step * 1e-3), "unit": "quartets/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": W.WORKLOADS.get(args.workload, args.workload), "nshell": bs.nshell, "nbf": bs.nbf,
+                       "cutoff": 5e-11, "scale_exchange": sx, "nvec": nvec, "densities": nvec * ncomp,
+                       "density": "synthetic general (non-symmetric) decaying, seed 7", "quartets_per_build": nq_step,
+                       "mrsf_builds_per_s": 1e3 / ms_per_step, "l2": "flushed between steps (256 MB fill)",
+                       "schwarz_setup_s": t_screen,
+                       "parallelism": f"bra shell pairs cyclic over {world} GPU(s), 1 NCCL all-reduce of f3"},
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "kernel": "eri_*_kernel family, MODE_GEN: Rys ERI + DMMA m8n8k4 multi-density digestion",
+                         "peak_source": "FP64 FMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                         "algorithmic_flops_per_step": flops_all / args.steps, "kernel_ms_per_step": kernel_ms / args.steps,
+                         "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peak_kind},
+            "e2e": {"value": nq_step / (e2e_ms / args.steps * 1e-3), "unit": "quartets/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            r = mrsf_cpu_sample(bs, d3, sx, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": r["quartets"] / r["seconds"], "unit": "quartets/s", "cores": r["cores"], "kind": "port",
+                                    "sample": f"every {r['stride']}-th bra shell pair, {r['quartets']} quartets in {r['seconds']:.1f} s"}
+        print(json.dumps(line))
+    drv.clean()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference binary cannot be built here
     (Fortran + network-only externals), so this times the oracle port with every host thread."""
@@ -120,13 +281,17 @@ def run_reference(args):
         return
     from openqp_b200 import workloads as W
     mol, bs = W.build(args.workload)
-    d = W.synthetic_density(bs)
-    from openqp_b200.scf import pack
-    dp = pack(d)
     sx = W.scale_exchange(args.workload)
+    if args.workload in MRSF_WORKLOADS:
+        dp = W.mrsf_densities(bs, args.nvec)
+        sampler = mrsf_cpu_sample
+    else:
+        from openqp_b200.scf import pack
+        dp = pack(W.synthetic_density(bs))
+        sampler = cpu_sample
     times, quartets, stride, cores = [], 0, 1, 1
     for it in range(args.warmup + args.steps):
-        r = cpu_sample(bs, dp, sx, args.cpu_seconds if it >= args.warmup else min(args.cpu_seconds, 3.0))
+        r = sampler(bs, dp, sx, args.cpu_seconds if it >= args.warmup else min(args.cpu_seconds, 3.0))
         if it >= args.warmup:
             times.append(r["seconds"]); quartets += r["quartets"]; stride = r["stride"]; cores = r["cores"]
     tot = sum(times)
@@ -148,6 +313,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload in MRSF_WORKLOADS:
+        return main_mrsf(args)
     import torch
     import torch.distributed as dist
     from openqp_b200 import workloads as W

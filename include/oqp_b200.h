@@ -91,6 +91,11 @@ int oqpb_jk_td(oqpb_ctx* ctx, const double* d2, int nvec, int flags, double scal
  * f3(v,c,:,:) = sc*J[d3(v,c)] (c <= 4) - se*K[d3(v,c)] (all c); d3, f3: (nvec, ncomp, nbf, nbf).      */
 int oqpb_jk_mrsf(oqpb_ctx* ctx, const double* d3, int nvec, int ncomp, double scale_exchange,
                  double scale_coulomb, double* f3, long long* nskipped);
+/* same with DEVICE pointers (d3_dev, f3_dev: nvec*ncomp*nbf*nbf doubles each, f3_dev is overwritten): the Davidson
+ * trial densities and their Fock-like matrices stay in HBM between iterations (the sigma session of
+ * routec_sig_iter, routec_sig.F90:28-56, would sit on this entry).                                     */
+int oqpb_jk_mrsf_dev(oqpb_ctx* ctx, const double* d3_dev, int nvec, int ncomp, double scale_exchange,
+                     double scale_coulomb, double* f3_dev);
 
 /* ---- introspection used by the parity tests and the benchmark ------------------------------------- */
 /* statistics of the last build: [0] surviving shell quartets, [1] skipped (nschwz), [2] primitive

@@ -1339,6 +1339,12 @@ __host__ __device__ constexpr int small_regcap() {
   return (key == 2010 || key == 2100 || key == 1100 || key == 1010 || key == 3000) ? 128 : OQPB_SMALL_REGS;
 }
 
+// MODE_GEN staging of the thread-per-quartet kernels: blocks of a warp staged at a time (power of two, at most 96 KB / CTA)
+__host__ __device__ constexpr int gen_sub(int ntot, int nwarps) {
+  int sub = 32;
+  while (sub > 4 && (size_t)nwarps * sub * (ntot | 1) * 8 > 96 * 1024) sub /= 2;
+  return sub;
+}
 // Rys evaluation state at X shared by all roots and weights of a primitive quartet
 struct RysX {
   bool asym;
@@ -1602,20 +1608,28 @@ eri_small_kernel(const EriArgs A) {
       digest_sym_reg<N0, N1, N2, N3, !GS, DEN_BATCH>(A, blk, pb.oa, pb.ob, pk.oa, pk.ob, mbra, mc, den0, DEN_EARLY);
     } else {
       // MODE_GEN: the 32 blocks of the warp go to shared memory and are digested one after the other by all lanes
-      constexpr int GBS = NTOT | 1;
+      // (GEN_SUB blocks per warp at a time, so that the staging area stays small and the occupancy is kept)
+      constexpr int GBS = NTOT | 1, SUB = gen_sub(NTOT, NTH / 32);
       double* wb = gsm + (GS ? 3 * NIJ1 * NKL1 * NTH : (RSM ? RysSmem<R>::doubles(A.rys_xmax) : 0)) +
-                   (size_t)(threadIdx.x >> 5) * (32 * GBS);
-      __syncwarp();
+                   (size_t)(threadIdx.x >> 5) * (SUB * GBS);
+      const unsigned live_all = __ballot_sync(0xffffffffu, valid && any);
+#pragma unroll 1
+      for (int h = 0; h < 32 / SUB; ++h) {
+        unsigned live = live_all & (unsigned)(((1ull << SUB) - 1ull) << (h * SUB));
+        if (live == 0) continue;
+        __syncwarp();
+        if (lane / SUB == h) {
 #pragma unroll
-      for (int e = 0; e < NTOT; ++e) wb[lane * GBS + e] = blk[e];
-      __syncwarp();
-      unsigned live = __ballot_sync(0xffffffffu, valid && any);
-      while (live) {
-        const int q = __ffs(live) - 1;
-        live &= live - 1;
-        const int off[4] = {__shfl_sync(0xffffffffu, pb.oa, q), __shfl_sync(0xffffffffu, pb.ob, q),
-                            __shfl_sync(0xffffffffu, pk.oa, q), __shfl_sync(0xffffffffu, pk.ob, q)};
-        digest_gen_warp<N0, N1, N2, N3>(A, wb + q * GBS, off, lane);
+          for (int e = 0; e < NTOT; ++e) wb[(lane % SUB) * GBS + e] = blk[e];
+        }
+        __syncwarp();
+        while (live) {
+          const int q = __ffs(live) - 1;
+          live &= live - 1;
+          const int off[4] = {__shfl_sync(0xffffffffu, pb.oa, q), __shfl_sync(0xffffffffu, pb.ob, q),
+                              __shfl_sync(0xffffffffu, pk.oa, q), __shfl_sync(0xffffffffu, pk.ob, q)};
+          digest_gen_warp<N0, N1, N2, N3>(A, wb + (q % SUB) * GBS, off, lane);
+        }
       }
     }
   }
@@ -2012,7 +2026,7 @@ cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
   if constexpr (Cfg::NCART4 <= SMALL_MAX) {
     constexpr int R = Cfg::R;
     constexpr int NTOT = Shell<LA, PV>::NOUT * Shell<LB, PV>::NOUT * Shell<LC, PV>::NOUT * Shell<LD, PV>::NOUT;
-    constexpr size_t gen = (size_t)(SMALL_NT / 32) * 32 * (NTOT | 1) * sizeof(double);  // MODE_GEN block staging
+    constexpr size_t gen = (size_t)(SMALL_NT / 32) * gen_sub(NTOT, SMALL_NT / 32) * (NTOT | 1) * sizeof(double);  // MODE_GEN block staging
     const size_t smem = (RysSmem<R>::USE ? (size_t)RysSmem<R>::doubles(args.rys_xmax) * sizeof(double) : 0) +
                         (args.mode == MODE_GEN ? gen : 0);
     static bool attr_set = false;
@@ -2026,7 +2040,7 @@ cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
     return cudaGetLastError();
   } else if constexpr (Cfg::NCART4 <= MEDIUM_MAX) {
     constexpr int NTOT = Shell<LA, PV>::NOUT * Shell<LB, PV>::NOUT * Shell<LC, PV>::NOUT * Shell<LD, PV>::NOUT;
-    constexpr size_t gen = (size_t)(MEDIUM_NT / 32) * 32 * (NTOT | 1) * sizeof(double);  // MODE_GEN block staging
+    constexpr size_t gen = (size_t)(MEDIUM_NT / 32) * gen_sub(NTOT, MEDIUM_NT / 32) * (NTOT | 1) * sizeof(double);  // MODE_GEN block staging
     constexpr size_t smem0 = (size_t)3 * Cfg::NIJ1 * Cfg::NKL1 * MEDIUM_NT * sizeof(double);
     const size_t smem = smem0 + (args.mode == MODE_GEN ? gen : 0);
     static bool attr_set = false;

@@ -1190,26 +1190,49 @@ int oqpb_jk_td(oqpb_ctx* ctx, const double* d2, int nvec, int flags, double se, 
   return OQPB_OK;
 }
 
+// d3 / f3 on the device (interleaved d3(v, c, mu, nu), v fastest)
+static int mrsf_core(oqpb_ctx* ctx, const double* d3_dev, double* f3_dev, int nvec, int ncomp, double se, double sc) {
+  const int ns = ctx->nshell, nbf = ctx->nbf;
+  const long npairs = (long)ns * (ns + 1) / 2;
+  const int NM = nvec * ncomp;
+  CK(cudaMemsetAsync(ctx->d_maxden.p, 0, 8, ctx->stream));
+  k_shlden_gen<<<(unsigned)((npairs + 127) / 128), 128, 0, ctx->stream>>>(
+      ns, npairs, ctx->d_aooff.as<int>(), ctx->d_naos.as<int>(), d3_dev, NM, nbf, ctx->d_dsh.as<double>(),
+      ctx->d_maxden.as<unsigned long long>());
+  CK(cudaGetLastError());
+  // Coulomb: cval * ds with ds = d3 + d3^T on (i,j),(j,i),(k,l),(l,k)  -> cj = sc; exchange xval -> ck = se
+  CK(cudaMemsetAsync(f3_dev, 0, (size_t)nbf * nbf * NM * sizeof(double), ctx->stream));
+  BuildSpec S;
+  S.mode = MODE_GEN;
+  S.Pgen = d3_dev;
+  S.Fgen = f3_dev;
+  S.gen_nm = NM; S.gen_ncoul = 4; S.gen_nvec = nvec;
+  S.cj = sc; S.ck = se;
+  S.digest_flops_per_int = 144.0 / 7.0 * NM;  // (4*4 + 8*7) * 2 flops per integral and vector
+  return run_build(ctx, S);
+}
+
+int oqpb_jk_mrsf_dev(oqpb_ctx* ctx, const double* d3_dev, int nvec, int ncomp, double se, double sc, double* f3_dev) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  cudaSetDevice(ctx->device);
+  if (nvec < 1 || ncomp < 4 || !d3_dev || !f3_dev) return OQPB_ERR_BAD_ARG;
+  return mrsf_core(ctx, d3_dev, f3_dev, nvec, ncomp, se, sc);
+}
+
 int oqpb_jk_mrsf(oqpb_ctx* ctx, const double* d3, int nvec, int ncomp, double se, double sc, double* f3,
                  long long* nskipped) {
   int rc = check_ready(ctx);
   if (rc) return rc;
   cudaSetDevice(ctx->device);
   if (nvec < 1 || ncomp < 4) return OQPB_ERR_BAD_ARG;
-  const int ns = ctx->nshell, nbf = ctx->nbf;
-  const long n2 = (long)nbf * nbf, npairs = (long)ns * (ns + 1) / 2;
+  const long n2 = (long)ctx->nbf * ctx->nbf;
   const int NM = nvec * ncomp;
   size_t bytes = (size_t)n2 * NM * sizeof(double);
   CK(ctx->d_gen_in.ensure(bytes));
   CK(ctx->d_gen_out.ensure(bytes));
   CK(cudaMemcpyAsync(ctx->d_gen_in.p, d3, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemsetAsync(ctx->d_maxden.p, 0, 8, ctx->stream));
-  k_shlden_gen<<<(unsigned)((npairs + 127) / 128), 128, 0, ctx->stream>>>(
-      ns, npairs, ctx->d_aooff.as<int>(), ctx->d_naos.as<int>(), ctx->d_gen_in.as<double>(), NM, nbf,
-      ctx->d_dsh.as<double>(), ctx->d_maxden.as<unsigned long long>());
-  CK(cudaGetLastError());
-  // Coulomb: cval * ds with ds = d3 + d3^T on (i,j),(j,i),(k,l),(l,k)  -> cj = sc; exchange xval -> ck = se
-  rc = gen_build(ctx, NM, 4, nvec, sc, se);
+  rc = mrsf_core(ctx, ctx->d_gen_in.as<double>(), ctx->d_gen_out.as<double>(), nvec, ncomp, se, sc);
   if (rc) return rc;
   CK(cudaMemcpyAsync(f3, ctx->d_gen_out.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));

@@ -135,6 +135,12 @@ class Int2Compute:
                                         C.c_int(nfocks), C.c_double(scale_exchange), C.c_double(scale_coulomb)),
                     "oqpb_fock_dev")
 
+    def mrsf_dev(self, d3_ptr: int, f3_ptr: int, nvec: int, ncomp: int = 7, scale_exchange=1.0, scale_coulomb=1.0):
+        """int2_mrsf_data_t with device-resident d3 / f3 (layout d3(v, c, mu, nu), v fastest)"""
+        self._check(lib().oqpb_jk_mrsf_dev(self._h, C.c_void_p(d3_ptr), C.c_int(nvec), C.c_int(ncomp),
+                                           C.c_double(scale_exchange), C.c_double(scale_coulomb), C.c_void_p(f3_ptr)),
+                    "oqpb_jk_mrsf_dev")
+
     def fock_post_dev(self, f_ptr: int, nfocks: int):
         self._check(lib().oqpb_fock_post_dev(self._h, C.c_void_p(f_ptr), C.c_int(nfocks)), "oqpb_fock_post_dev")
 

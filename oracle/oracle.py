@@ -126,14 +126,14 @@ class Oracle:
             lib().orc_td_post(C.c_int(nbf), C.c_int(nv), _p(apb))
         return np.transpose(apb, (0, 2, 1)).copy(), np.transpose(amb, (0, 2, 1)).copy(), st
 
-    def mrsf(self, d3, scale_exchange=1.0, scale_coulomb=1.0, nthreads=0):
+    def mrsf(self, d3, scale_exchange=1.0, scale_coulomb=1.0, nthreads=0, stride=1, offset=0):
         """int2_mrsf_data_t (tdhf_mrsf_lib.F90:8-26): d3 numpy (nvec, ncomp, nbf, nbf) [v,c,mu,nu];
         returns f3 same shape."""
         d3 = np.asarray(d3, dtype=np.float64)
         nv, nc, nbf, _ = d3.shape
         dF = np.ascontiguousarray(np.transpose(d3, (3, 2, 1, 0)))  # Fortran d3(v,c,mu,nu): v fastest
         f3 = np.zeros_like(dF)
-        st = self._run(MRSF, dF, nv, nc, scale_exchange, scale_coulomb, 0, f3, None, nthreads, 0, -1, 1, 0)
+        st = self._run(MRSF, dF, nv, nc, scale_exchange, scale_coulomb, 0, f3, None, nthreads, 0, -1, stride, offset)
         return np.transpose(f3, (3, 2, 1, 0)).copy(), st
 
     def quartet_list(self, d_packed, want_list=True):
