@@ -951,27 +951,31 @@ __device__ __forceinline__ void gen_contract(const EriArgs& A, const double* __r
       }
     }
   } else {
-    for (int e = lane; e < NO * mrows; e += 32) {
-      const int m = e % mrows, o = e / mrows;
+    // lanes over the matrices (m fastest: coalesced P reads and reds), outputs one after the other
+#pragma unroll 1
+    for (int o = 0; o < NO; ++o) {
       const int ix = o / N[Y], iy = o % N[Y];
       const double* v = blk + ix * STR[X] + iy * STR[Y];
-      double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-      for (int iu = 0; iu < N[U]; ++iu)
-#pragma unroll
-        for (int iv = 0; iv < N[V]; ++iv) {
-          const size_t p = (size_t)(off[U] + iu), q = (size_t)(off[V] + iv);
-          const double x = v[iu * STR[U] + iv * STR[V]];
-          s1 = fma(x, __ldg(P + (q * nbf + p) * NM + m), s1);
-          s2 = fma(x, __ldg(P + (p * nbf + q) * NM + m), s2);
-        }
       const size_t p = (size_t)(off[X] + ix), q = (size_t)(off[Y] + iy);
-      if constexpr (COUL) {
-        const double sj = s1 + s2;
-        if (sj != 0.0) { atomicAdd(F + (q * nbf + p) * NM + m, scale * sj); atomicAdd(F + (p * nbf + q) * NM + m, scale * sj); }
-      } else {
-        if (s1 != 0.0) atomicAdd(F + (q * nbf + p) * NM + m, scale * s1);
-        if (s2 != 0.0) atomicAdd(F + (p * nbf + q) * NM + m, scale * s2);
+#pragma unroll 1
+      for (int m = lane; m < mrows; m += 32) {
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int iu = 0; iu < N[U]; ++iu)
+#pragma unroll
+          for (int iv = 0; iv < N[V]; ++iv) {
+            const size_t pp = (size_t)(off[U] + iu), qq = (size_t)(off[V] + iv);
+            const double x = v[iu * STR[U] + iv * STR[V]];
+            s1 = fma(x, __ldg(P + (qq * nbf + pp) * NM + m), s1);
+            s2 = fma(x, __ldg(P + (pp * nbf + qq) * NM + m), s2);
+          }
+        if constexpr (COUL) {
+          const double sj = s1 + s2;
+          if (sj != 0.0) { atomicAdd(F + (q * nbf + p) * NM + m, scale * sj); atomicAdd(F + (p * nbf + q) * NM + m, scale * sj); }
+        } else {
+          if (s1 != 0.0) atomicAdd(F + (q * nbf + p) * NM + m, scale * s1);
+          if (s2 != 0.0) atomicAdd(F + (p * nbf + q) * NM + m, scale * s2);
+        }
       }
     }
   }
