@@ -521,15 +521,19 @@ int build_pairtable(oqpb_ctx* ctx, const Cutoffs& c, PairTable& T, const std::ve
         int j = id - i * (i + 1) / 2;
         return ctx->am[i] >= ctx->am[j] ? i : j;
       };
-      struct Key { int bin; int sa; double q; int id; };
+      struct Key { int bin; int pc; int sa; double q; int id; };
       std::vector<Key> key(v.size());
+      // ... and inside a bin first by primitive-pair count: the lanes of a warp (one quartet each) then run primitive
+      // loops of similar length (w32: -4 % build time); OQPB_SORT_PCNT=0 restores the pure shell order
+      static const int sort_pcnt = getenv("OQPB_SORT_PCNT") ? atoi(getenv("OQPB_SORT_PCNT")) : 1;
       for (size_t k = 0; k < v.size(); ++k) {
         double q = qof(v[k]);
         int e = q > 0 ? std::ilogb(q) : -100000;
-        key[k] = {e >= 0 ? e / 2 : -((-e + 1) / 2), first_shell(v[k]), q, v[k]};
+        key[k] = {e >= 0 ? e / 2 : -((-e + 1) / 2), sort_pcnt ? cnt[v[k]] : 0, first_shell(v[k]), q, v[k]};
       }
       std::sort(key.begin(), key.end(), [](const Key& a, const Key& b) {
         if (a.bin != b.bin) return a.bin > b.bin;
+        if (a.pc != b.pc) return a.pc > b.pc;
         if (a.sa != b.sa) return a.sa < b.sa;
         if (a.q != b.q) return a.q > b.q;
         return a.id < b.id;
@@ -713,7 +717,8 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
       std::vector<int> km(na, 0);
       // kets at or beyond km[p] cannot survive: suffix maxima of the ket list's bounds are monotone
       const double* Qs = T.Qsuf.data() + T.cls_off[pcb];
-      for (int p = 0; p < na; ++p) {
+#pragma omp parallel for schedule(static) if (na > 4096)
+      for (int p = rk; p < na; p += nr) {  // this rank's bras only
         int lo = 0, hi = nb;  // first k with Qa[p] * Qs[k] * bound4 < cutoff
         while (lo < hi) {
           int mid = (lo + hi) / 2;
