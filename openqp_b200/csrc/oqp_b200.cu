@@ -138,11 +138,13 @@ struct oqpb_ctx {
   std::vector<double> Qmat;  // nshell x nshell (host)
   DevBuf d_Qmat, d_dsh, d_maxden, d_ok, d_d4, d_rowsbuf;
   // work
-  static constexpr int NSTREAM = 4;  // launch lanes: chunk c runs on lane c % NSTREAM (own task buffer) so that the
+  static constexpr int NSTREAM = 8;  // launch lanes (nlanes of them used): chunk c runs on lane c % NSTREAM (own task buffer) so that the
                                      // tail of one class kernel overlaps the next enumeration / class kernel
   DevBuf d_tasks[NSTREAM], d_counters, d_Dsq, d_F, d_Din, d_stats, d_gen_in, d_gen_out;
-  cudaStream_t lane[NSTREAM] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t lane_ev[NSTREAM] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t lane[NSTREAM] = {};
+  cudaEvent_t lane_ev[NSTREAM] = {};
+  int nlanes = 4;      // OQPB_NLANES
+  int grid_pct = 100;  // OQPB_GRID_PCT: scales the per-class grid caps
   cudaEvent_t fork_ev = nullptr;
   size_t task_cap = (size_t)1 << 23;
   int rank = 0, nranks = 1;
@@ -767,7 +769,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   CK(ctx->d_counters.ensure((3 * nch + 4) * sizeof(unsigned long long)));
   CK(cudaMemsetAsync(ctx->d_counters.p, 0, (3 * nch + 4) * sizeof(unsigned long long), ctx->stream));
   unsigned* d_cnt = ctx->d_counters.as<unsigned>();  // [2*c] = ntasks, [2*c+1] = fetch counter
-  const int nlane = ctx->profile || ctx->record ? 1 : oqpb_ctx::NSTREAM;
+  const int nlane = ctx->profile || ctx->record ? 1 : ctx->nlanes;
   for (int l = 0; l < nlane; ++l) CK(ctx->d_tasks[l].ensure(ctx->task_cap * sizeof(int2)));
   CK(ctx->d_stats.ensure((2 * nch + 2) * sizeof(unsigned long long)));
   CK(cudaMemsetAsync(ctx->d_stats.p, 0, (2 * nch + 2) * sizeof(unsigned long long), ctx->stream));
@@ -821,7 +823,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     A.Pgen = S.Pgen; A.Fgen = S.Fgen; A.gen_nmat_total = S.gen_nm; A.gen_ncoul = S.gen_ncoul; A.gen_nvec = S.gen_nvec;
     const int qcls = quartet_class(pc_of(ch.pca), pc_of(ch.pcb));
     const ClassEntry& ce = tab[qcls];
-    size_t nb = std::min<size_t>((ch.cand + ce.qpb - 1) / ce.qpb, (size_t)ce.maxcta);
+    size_t nb = std::min<size_t>((ch.cand + ce.qpb - 1) / ce.qpb, (size_t)ce.maxcta * ctx->grid_pct / 100);
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (ctx->profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, cs); }
     CK(ce.launch(A, (int)std::max<size_t>(nb, 1), cs));
@@ -930,6 +932,10 @@ int oqpb_ctx_create(oqpb_ctx** out, int device) {
     cudaStreamCreateWithFlags(&ctx->lane[l], cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->lane_ev[l], cudaEventDisableTiming);
   }
+  // tuning knobs (tools/sweep_knobs.sh)
+  if (const char* e = getenv("OQPB_NLANES")) ctx->nlanes = std::max(1, std::min((int)oqpb_ctx::NSTREAM, atoi(e)));
+  if (const char* e = getenv("OQPB_GRID_PCT")) ctx->grid_pct = std::max(10, atoi(e));
+  if (const char* e = getenv("OQPB_TASK_CAP_LOG2")) ctx->task_cap = (size_t)1 << std::max(16, std::min(28, atoi(e)));
   // Rys tables
   if (ctx->d_rys.ensure(sizeof(RYS_TAB_H)) != cudaSuccess) { delete ctx; return OQPB_ERR_CUDA; }
   cudaMemcpy(ctx->d_rys.p, RYS_TAB_H, sizeof(RYS_TAB_H), cudaMemcpyHostToDevice);
