@@ -1686,7 +1686,7 @@ eri_group_kernel(const EriArgs A) {
   using Cfg = ClassCfg<LA, LB, LC, LD>;
   using GC = GroupCfg<LA, LB, LC, LD>;
   constexpr int R = Cfg::R, NA = Cfg::NA, NB = Cfg::NB, NC = Cfg::NC, ND = Cfg::ND, NKET = Cfg::NKET;
-  constexpr int NMAX = Cfg::NMAX, MMAX = Cfg::MMAX, NKL1 = Cfg::NKL1;
+  constexpr int NMAX = Cfg::NMAX, MMAX = Cfg::MMAX, NKL1 = Cfg::NKL1, NIJ1 = Cfg::NIJ1;
   constexpr int G1 = Cfg::G1, G2 = Cfg::G2, GSTR = GC::GSTR, GOFF = GC::GOFF, QSM = GC::QSMG;
   constexpr int G = GC::G, NVL = GC::NVL, QPW = GC::QPW, VL = GC::VL;
   constexpr int LCAP = 64;
@@ -1711,7 +1711,7 @@ eri_group_kernel(const EriArgs A) {
     int ax, ay, az, bx, by, bz;
     cart_xyz_rt(LA, ia, ax, ay, az);
     cart_xyz_rt(LB, ib, bx, by, bz);
-    obx[j] = (ax * (LB + 1) + bx) * NKL1; oby[j] = (ay * (LB + 1) + by) * NKL1; obz[j] = (az * (LB + 1) + bz) * NKL1;
+    obx[j] = ax * (LB + 1) + bx; oby[j] = ay * (LB + 1) + by; obz[j] = az * (LB + 1) + bz;  // table layout [c][d][a][b]
   }
   const unsigned ntasks = *A.ntasks;
   unsigned long long st_prim = 0, st_ints = 0;
@@ -1858,13 +1858,13 @@ eri_group_kernel(const EriArgs A) {
 #pragma unroll
               for (int k = 0; k < NKL1; ++k) {
 #pragma unroll
-                for (int a = 0; a <= LA; ++a) S3[(a * (LB + 1)) * NKL1 + k] = h[a][k];
+                for (int a = 0; a <= LA; ++a) S3[k * NIJ1 + a * (LB + 1)] = h[a][k];
 #pragma unroll
                 for (int b = 1; b <= LB; ++b) {
 #pragma unroll
                   for (int n = 0; n < NMAX - b; ++n) h[n][k] = h[n + 1][k] + ABd * h[n][k];
 #pragma unroll
-                  for (int a = 0; a <= LA; ++a) S3[(a * (LB + 1) + b) * NKL1 + k] = h[a][k];
+                  for (int a = 0; a <= LA; ++a) S3[k * NIJ1 + a * (LB + 1) + b] = h[a][k];
                 }
               }
             } else {
@@ -1893,10 +1893,10 @@ eri_group_kernel(const EriArgs A) {
               }
             }
             for (int k = 0; k < NKL1; ++k) {
-              for (int a = 0; a <= LA; ++a) S3[(a * (LB + 1)) * NKL1 + k] = S2[a * NKL1 + k];
+              for (int a = 0; a <= LA; ++a) S3[k * NIJ1 + a * (LB + 1)] = S2[a * NKL1 + k];
               for (int b = 1; b <= LB; ++b) {
                 for (int n = 0; n < NMAX - b; ++n) S2[n * NKL1 + k] = S2[(n + 1) * NKL1 + k] + ABd * S2[n * NKL1 + k];
-                for (int a = 0; a <= LA; ++a) S3[(a * (LB + 1) + b) * NKL1 + k] = S2[a * NKL1 + k];
+                for (int a = 0; a <= LA; ++a) S3[k * NIJ1 + a * (LB + 1) + b] = S2[a * NKL1 + k];
               }
             }
             }
@@ -1917,7 +1917,8 @@ eri_group_kernel(const EriArgs A) {
                 const double* gz = gbase + 2 * GSTR + obz[j];
                 double X_[NKL1], Y_[NKL1], Z_[NKL1];
 #pragma unroll
-                for (int k = 0; k < NKL1; ++k) { X_[k] = gx[k]; Y_[k] = gy[k]; Z_[k] = gz[k]; }
+                // [c][d][a][b] layout: the lanes of a group (different a,b) read neighbouring words, no bank conflicts
+                for (int k = 0; k < NKL1; ++k) { X_[k] = gx[k * NIJ1]; Y_[k] = gy[k * NIJ1]; Z_[k] = gz[k * NIJ1]; }
                 static_for<0, NKET>([&](auto I) {
                   constexpr int k = decltype(I)::value;
                   constexpr int ic = k / ND, id = k % ND;
