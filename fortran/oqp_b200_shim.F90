@@ -49,6 +49,11 @@ module oqp_b200_shim
       real(c_double), intent(in) :: d3(*); real(c_double), intent(out) :: f3(*)
       real(c_double), value :: se, sc; integer(c_long_long), intent(out) :: nskipped
     end function
+    !> device-resident variant (d3_dev, f3_dev = CUDA device pointers, e.g. from a routec_sig session)
+    integer(c_int) function oqpb_jk_mrsf_dev(ctx, d3_dev, nvec, ncomp, se, sc, f3_dev) bind(C, name="oqpb_jk_mrsf_dev")
+      import; type(c_ptr), value :: ctx, d3_dev, f3_dev; integer(c_int), value :: nvec, ncomp
+      real(c_double), value :: se, sc
+    end function
   end interface
 
   !> Same public surface as int2_compute_t (int2.F90:137-185): init / set_screening / set_cutoff / clean, `skipped`;
