@@ -282,3 +282,51 @@ def test_full_size_properties_c20h42(drv):
     c = drv.run(Int2TdData(d1[None], tamm_dancoff=True, tamm_dancoff_coulomb=True))
     # TDA amb = J[P+P^T] - K[P]  (= 2J - K for symmetric P) ;  RHF f = J - K/2
     assert np.abs(c.amb[0] - 2 * unpack(f1, bs.nbf)).max() < 2e-9
+
+
+def test_mrsf_device_entry_matches_host_entry(drv):
+    """oqpb_jk_mrsf_dev (device-resident d3 / f3) against oqpb_jk_mrsf (host buffers) on the same input."""
+    import torch
+    from openqp_b200.int2 import Int2MrsfData
+    bs = B.BasisSet(B.water_dimer(), "6-31g(d)")
+    drv.init(bs)
+    drv.set_screening()
+    rng = np.random.default_rng(5)
+    d3 = rng.normal(size=(2, 7, bs.nbf, bs.nbf)) * 0.1
+    host = drv.run(Int2MrsfData(d3, scale_exchange=0.5, scale_coulomb=1.0)).f3
+    dF = np.ascontiguousarray(np.transpose(d3, (3, 2, 1, 0)))
+    d_dev = torch.from_numpy(dF).cuda()
+    f_dev = torch.full_like(d_dev, 7.0)  # must be overwritten, not accumulated into
+    drv.mrsf_dev(d_dev.data_ptr(), f_dev.data_ptr(), 2, 7, scale_exchange=0.5, scale_coulomb=1.0)
+    drv.synchronize()
+    torch.cuda.synchronize()
+    dev = np.transpose(f_dev.cpu().numpy(), (3, 2, 1, 0))
+    assert np.abs(dev - host).max() < 1e-12
+
+
+def test_full_size_properties_w32_and_mrsf(drv):
+    """Headline workload ((H2O)32 cc-pVTZ 5d/7f, 1856 bf: every s..f class, group and team kernels) and the batched
+    multi-density consumer at that size: linearity of the SYM build, and MRSF components of a symmetric density against
+    the RHF build of the same density (c <= 4: J - K = F_rhf with scale_exchange 2;  c > 4: -K)."""
+    from openqp_b200.int2 import Int2MrsfData, Int2RhfData
+    mol, bs = B.build("w32")
+    drv.init(bs)
+    drv.set_screening()
+    d1, d2 = decaying_density(bs, 1), decaying_density(bs, 2)
+    f1 = drv.run(Int2RhfData(pack(d1), post=True)).f[0]
+    f2 = drv.run(Int2RhfData(pack(d2), post=True)).f[0]
+    f12 = drv.run(Int2RhfData(pack(d1 - 0.5 * d2), post=True)).f[0]
+    assert np.abs(f12 - (f1 - 0.5 * f2)).max() < 1e-9
+    fk = drv.run(Int2RhfData(pack(d1), scale_coulomb=0.0, post=True)).f[0]
+    mol5, bs5 = B.build("c3")
+    drv.init(bs5, 1e-12)
+    drv.set_screening()
+    d = decaying_density(bs5, 3)
+    fr = drv.run(Int2RhfData(pack(d), scale_exchange=2.0, post=True)).f[0]  # J - K
+    frk = drv.run(Int2RhfData(pack(d), scale_coulomb=0.0, post=True)).f[0]  # -K/2
+    d3 = np.broadcast_to(d, (1, 7, bs5.nbf, bs5.nbf)).copy()
+    f3 = drv.run(Int2MrsfData(d3, scale_exchange=1.0, scale_coulomb=1.0)).f3
+    assert np.abs(f3[0, 0] - unpack(fr, bs5.nbf)).max() < 2e-9
+    assert np.abs(f3[0, 3] - f3[0, 0]).max() < 1e-10
+    assert np.abs(f3[0, 6] - 2 * unpack(frk, bs5.nbf)).max() < 2e-9
+    assert np.isfinite(fk).all()
