@@ -1349,19 +1349,41 @@ __host__ __device__ constexpr int gen_sub(int ntot, int nwarps) {
   while (sub > 4 && (size_t)nwarps * sub * (ntot | 1) * 8 > 96 * 1024) sub /= 2;
   return sub;
 }
+// software-pipelined primitive loads (24 more registers): measured per class on (H2O)32/cc-pVTZ
+template <int LA, int LB, int LC, int LD>
+__host__ __device__ constexpr bool prim_pipe() {
+#ifdef OQPB_PRIM_PIPE
+  return OQPB_PRIM_PIPE != 0;
+#else
+  constexpr int key = LA * 1000 + LB * 100 + LC * 10 + LD;
+  return key == 0 || key == 2000 || key == 1110 || key == 3010 || key == 3100 || key == 2020 || key == 2200;
+#endif
+}
 // Rys evaluation state at X shared by all roots and weights of a primitive quartet
 struct RysX {
   bool asym;
   int iv;
   double rx, rs, t;
 };
+// 1/sqrt(x) for normal positive x: hardware seed (rsqrt.approx.f64, ~2^-22) + two Newton steps; the library
+// rsqrt() with its special-case handling was 16 % of the instructions of the contracted s/p launches
+__device__ __forceinline__ double rsqrt_nr(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  return y;
+}
 __device__ __forceinline__ RysX rys_prepare(const EriArgs& a, double X) {
   RysX s;
   s.asym = X >= (double)a.rys_xmax;
   s.iv = 0;
   s.rx = s.rs = s.t = 0.0;
   if (s.asym) {
-    s.rs = rsqrt(X);  // half-range Gauss-Hermite asymptote (rys.F90:2711-2713): r = h_r / X, w = h_w / sqrt(X)
+    s.rs = rsqrt_nr(X);  // half-range Gauss-Hermite asymptote (rys.F90:2711-2713): r = h_r / X, w = h_w / sqrt(X)
     s.rx = s.rs * s.rs;
   } else {
     s.iv = (int)X;
@@ -1462,24 +1484,45 @@ eri_small_kernel(const EriArgs A) {
     const double thr = A.prim_cutoff * (1.0 - 1e-9) * (pb.zmin + pk.zmin);
     double da0 = 0.0;
     if (pb.pcnt > 0) { const double* p0 = A.prim + (size_t)pb.poff * PRIM_STRIDE; da0 = __ldg(p0 + 4); }
+    // the primitive records of the NEXT iteration are loaded before the body of the current one (software pipeline:
+    // the L1 latency of these small dependent loads was 30 % of the stall samples of the contracted launches)
+    const double2* pq0 = reinterpret_cast<const double2*>(A.prim + (size_t)pk.poff * PRIM_STRIDE);
+    const double2* pp0 = reinterpret_cast<const double2*>(A.prim + (size_t)pb.poff * PRIM_STRIDE);
+    constexpr bool PIPE = prim_pipe<LA, LB, LC, LD>();
+    double2 nq01 = make_double2(0, 0), nq23 = nq01, nq45 = nq01;
+    if (PIPE && pk.pcnt > 0) { nq01 = __ldg(pq0); nq23 = __ldg(pq0 + 1); nq45 = __ldg(pq0 + 2); }
     for (int kq = 0; kq < pk.pcnt; ++kq) {
-      const double2* pq = reinterpret_cast<const double2*>(A.prim + (size_t)(pk.poff + kq) * PRIM_STRIDE);
-      const double2 q01 = __ldg(pq), q23 = __ldg(pq + 1), q45 = __ldg(pq + 2);
+      if constexpr (!PIPE) { const double2* pq = pq0 + 3 * kq; nq01 = __ldg(pq); nq23 = __ldg(pq + 1); nq45 = __ldg(pq + 2); }
+      const double2 q01 = nq01, q23 = nq23, q45 = nq45;
+      if (PIPE && kq + 1 < pk.pcnt) {
+        const double2* pq = pq0 + 3 * (kq + 1);
+        nq01 = __ldg(pq); nq23 = __ldg(pq + 1); nq45 = __ldg(pq + 2);
+      }
       const double Qx = q01.x, Qy = q01.y, Qz = q23.x, eta = q23.y, db = q45.x, einv = q45.y;
       if ((da0 * db) * (da0 * db) < thr) break;
+      double2 np01 = make_double2(0, 0), np23 = np01, np45 = np01;
+      if (PIPE && pb.pcnt > 0) { np01 = __ldg(pp0); np23 = __ldg(pp0 + 1); np45 = __ldg(pp0 + 2); }
       for (int kp = 0; kp < pb.pcnt; ++kp) {
-        const double2* pp = reinterpret_cast<const double2*>(A.prim + (size_t)(pb.poff + kp) * PRIM_STRIDE);
-        const double2 p23 = __ldg(pp + 1), p45 = __ldg(pp + 2);
+        double2 p01 = np01, p23 = np23, p45 = np45;
+        if constexpr (PIPE) {
+          if (kp + 1 < pb.pcnt) {
+            const double2* pp = pp0 + 3 * (kp + 1);
+            np01 = __ldg(pp); np23 = __ldg(pp + 1); np45 = __ldg(pp + 2);
+          }
+        } else {
+          const double2* pp = pp0 + 3 * kp;
+          p23 = __ldg(pp + 1); p45 = __ldg(pp + 2);
+        }
         const double zeta = p23.y, zinv = p45.y;
         const double pfac = p45.x * db;
         if (pfac * pfac < thr) break;
         const double ab = zeta + eta;
         if (pfac * pfac < A.prim_cutoff * ab) continue;  // int_rys.F90:229-232
-        const double2 p01 = __ldg(pp);
+        if constexpr (!PIPE) p01 = __ldg(pp0 + 3 * kp);
         const double Px = p01.x, Py = p01.y, Pz = p23.x;
         any = true;
         ++st_prim;
-        const double rsab = rsqrt(ab);
+        const double rsab = rsqrt_nr(ab);
         const double abinv = rsab * rsab;
         const double rho = zeta * eta * abinv;
         const double PQ[3] = {Px - Qx, Py - Qy, Pz - Qz};
