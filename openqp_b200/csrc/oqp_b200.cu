@@ -11,6 +11,7 @@
 //   k_fock_post                  fock_jk post-scaling                             scf_addons.F90:1177-1185
 // There is no CPU fallback: every compute entry needs a CUDA device.
 #include <cuda_runtime.h>
+#include <chrono>
 
 #include <algorithm>
 #include <cmath>
@@ -117,6 +118,20 @@ double fprim_model(int l1, int l2, int l3, int l4) {
 
 }  // namespace
 
+// Work plan of a build: per (bra list, ket list) the ket bound index of every bra of this rank and the launch chunks.
+// It depends on the density only through 4*max|D| rounded UP to a power of two (a larger bound only admits more
+// candidates to the exact test in k_enum), so consecutive SCF iterations reuse it: no host planning, no upload.
+struct PlanChunk { int pca, pcb, p0, p1; size_t cand; };
+struct BuildPlan {
+  bool valid = false;
+  double bound4 = -1.0;
+  long gen = -1;
+  std::vector<PlanChunk> chunks;
+  std::vector<size_t> km_off;
+  std::vector<std::pair<int, int>> cps;
+  long long total_local = 0;
+};
+
 struct oqpb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -158,6 +173,8 @@ struct oqpb_ctx {
   unsigned* h_counts = nullptr;  // pinned
   size_t h_counts_cap = 0;
   double fp64_peak = 0;
+  BuildPlan plan;
+  long plan_gen = 0;  // bumped by set_basis / set_cutoff / set_screening / set_partition
 };
 
 // ===================================================================================== device kernels
@@ -695,70 +712,86 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
       nent, T.d_ent.as<PairEntry>(), T.d_Q.as<double>(), ctx->d_dsh.as<double>(), ns,
       ctx->d_maxden.as<unsigned long long>(), cutoff, ctx->d_ok.as<int>(), ctx->d_d4.as<double>());
   CK(cudaGetLastError());
+  static const bool timing = getenv("OQPB_TIMING") != nullptr;
+  auto tnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = tnow();
   double maxden = 0;
   CK(cudaMemcpyAsync(&maxden, ctx->d_maxden.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  const double t_synced = tnow();
   const double bound4 = 4.0 * maxden;
 
-  // ---- plan: per class pair, kmax[p] by a two-pointer sweep over the Q-sorted lists, chunk boundaries
-  struct Chunk { int pca, pcb, p0, p1; size_t cand; };
-  std::vector<Chunk> chunks;
-  std::vector<int> kmax(nent, 0);  // per bra entry, for the ket class currently planned -> stored per class pair
-  std::vector<std::vector<int>> kmax_all;  // index by class pair order
-  std::vector<std::pair<int, int>> cps;
-  long long total_local = 0;
+  // ---- plan (cached, see BuildPlan): per list pair, kmax[p] by binary search over the suffix maxima of the ket
+  // list's Schwarz bounds; chunk boundaries
+  using Chunk = PlanChunk;
   const int nr = ctx->nranks, rk = ctx->rank;
-  for (int pca = 0; pca < NL; ++pca) {  // pca / pcb are pair LISTS here (class x contraction bucket)
-    int na = T.cls_off[pca + 1] - T.cls_off[pca];
-    if (na == 0) continue;
-    for (int pcb = 0; pcb <= pca; ++pcb) {
-      int nb = T.cls_off[pcb + 1] - T.cls_off[pcb];
-      if (nb == 0) continue;
-      const double* Qa = T.Q.data() + T.cls_off[pca];
-      const double* Qb = T.Q.data() + T.cls_off[pcb];
-      std::vector<int> km(na, 0);
-      // kets at or beyond km[p] cannot survive: suffix maxima of the ket list's bounds are monotone
-      const double* Qs = T.Qsuf.data() + T.cls_off[pcb];
-#pragma omp parallel for schedule(static) if (na > 4096)
-      for (int p = rk; p < na; p += nr) {  // this rank's bras only
-        int lo = 0, hi = nb;  // first k with Qa[p] * Qs[k] * bound4 < cutoff
-        while (lo < hi) {
-          int mid = (lo + hi) / 2;
-          if ((Qa[p] * Qs[mid]) * bound4 < cutoff) hi = mid; else lo = mid + 1;
-        }
-        km[p] = lo;
-      }
-      (void)Qb;
-      // chunking over this rank's bras (p % nranks == rank)
-      size_t cand = 0;
-      int p0 = 0;
-      bool diag = pca == pcb;
-      for (int p = 0; p < na; ++p) {
-        if (p % nr != rk) continue;
-        total_local += diag ? (p + 1) : nb;
-        size_t c = diag ? (size_t)std::min(km[p], p + 1) : (size_t)km[p];
-        if (cand + c > ctx->task_cap && cand > 0) {
-          chunks.push_back({pca, pcb, p0, p, cand});
-          p0 = p;
-          cand = 0;
-        }
-        cand += c;
-      }
-      if (cand > 0) chunks.push_back({pca, pcb, p0, na, cand});
-      kmax_all.push_back(std::move(km));
-      cps.push_back({pca, pcb});
-    }
-  }
-  // upload kmax arrays (concatenated)
-  std::vector<int> km_cat;
-  std::vector<size_t> km_off(cps.size());
-  for (size_t c = 0; c < cps.size(); ++c) {
-    km_off[c] = km_cat.size();
-    km_cat.insert(km_cat.end(), kmax_all[c].begin(), kmax_all[c].end());
-  }
+  double bound4p = bound4;
+  if (bound4 > 0) { int e; std::frexp(bound4, &e); bound4p = std::ldexp(1.0, e); }  // next power of two >= bound4
+  BuildPlan& P = ctx->plan;
   DevBuf& d_km = ctx->d_rowsbuf;
   int rc;
-  if ((rc = upload(ctx, d_km, km_cat))) return rc;
+  double t_planned = tnow(), t_uploaded = t_planned;
+  size_t km_count = 0;
+  if (!(P.valid && P.gen == ctx->plan_gen && P.bound4 == bound4p)) {
+    P.valid = false;
+    P.chunks.clear(); P.cps.clear(); P.km_off.clear(); P.total_local = 0;
+    std::vector<std::vector<int>> kmax_all;  // index by list pair order
+    for (int pca = 0; pca < NL; ++pca) {  // pca / pcb are pair LISTS here (class x contraction bucket)
+      int na = T.cls_off[pca + 1] - T.cls_off[pca];
+      if (na == 0) continue;
+      for (int pcb = 0; pcb <= pca; ++pcb) {
+        int nb = T.cls_off[pcb + 1] - T.cls_off[pcb];
+        if (nb == 0) continue;
+        const double* Qa = T.Q.data() + T.cls_off[pca];
+        std::vector<int> km(na, 0);
+        // kets at or beyond km[p] cannot survive: suffix maxima of the ket list's bounds are monotone
+        const double* Qs = T.Qsuf.data() + T.cls_off[pcb];
+#pragma omp parallel for schedule(static) if (na > 4096)
+        for (int p = rk; p < na; p += nr) {  // this rank's bras only
+          int lo = 0, hi = nb;  // first k with Qa[p] * Qs[k] * bound4p < cutoff
+          while (lo < hi) {
+            int mid = (lo + hi) / 2;
+            if ((Qa[p] * Qs[mid]) * bound4p < cutoff) hi = mid; else lo = mid + 1;
+          }
+          km[p] = lo;
+        }
+        // chunking over this rank's bras (p % nranks == rank)
+        size_t cand = 0;
+        int p0 = 0;
+        bool diag = pca == pcb;
+        for (int p = 0; p < na; ++p) {
+          if (p % nr != rk) continue;
+          P.total_local += diag ? (p + 1) : nb;
+          size_t c = diag ? (size_t)std::min(km[p], p + 1) : (size_t)km[p];
+          if (cand + c > ctx->task_cap && cand > 0) {
+            P.chunks.push_back({pca, pcb, p0, p, cand});
+            p0 = p;
+            cand = 0;
+          }
+          cand += c;
+        }
+        if (cand > 0) P.chunks.push_back({pca, pcb, p0, na, cand});
+        kmax_all.push_back(std::move(km));
+        P.cps.push_back({pca, pcb});
+      }
+    }
+    // upload kmax arrays (concatenated)
+    std::vector<int> km_cat;
+    P.km_off.resize(P.cps.size());
+    for (size_t c = 0; c < P.cps.size(); ++c) {
+      P.km_off[c] = km_cat.size();
+      km_cat.insert(km_cat.end(), kmax_all[c].begin(), kmax_all[c].end());
+    }
+    km_count = km_cat.size();
+    t_planned = tnow();
+    if ((rc = upload(ctx, d_km, km_cat))) return rc;
+    t_uploaded = tnow();
+    P.bound4 = bound4p; P.gen = ctx->plan_gen; P.valid = true;
+  }
+  const std::vector<Chunk>& chunks = P.chunks;
+  const std::vector<std::pair<int, int>>& cps = P.cps;
+  const std::vector<size_t>& km_off = P.km_off;
+  const long long total_local = P.total_local;
   auto cp_index = [&](int pca, int pcb) {
     for (size_t c = 0; c < cps.size(); ++c) if (cps[c].first == pca && cps[c].second == pcb) return c;
     return (size_t)0;
@@ -858,6 +891,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
       CK(cudaStreamWaitEvent(ctx->stream, ctx->lane_ev[l], 0));
     }
   }
+  const double t_launched = tnow();
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   if (nch) CK(cudaMemcpyAsync(ctx->h_counts, d_cnt, 2 * nch * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
   if (nch) CK(cudaMemcpyAsync(h_stats.data(), ctx->d_stats.p, 2 * nch * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -865,6 +899,10 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->st_kernel_ms = ms;
+  if (timing)
+    fprintf(stderr, "[oqpb timing] wait maxden %.2f ms, plan %.2f, upload kmax (%zu ints) %.2f, launch loop %.2f, drain %.2f; device %.2f ms, %zu chunks\n",
+            t_synced - t_begin, t_planned - t_synced, km_count, t_uploaded - t_planned, t_launched - t_uploaded,
+            tnow() - t_launched, ms, nch);
   long long surv = 0;
   double flops = 0;
   for (size_t c = 0; c < nch; ++c) {
@@ -1002,6 +1040,7 @@ int oqpb_set_basis(oqpb_ctx* ctx, int nshell, int nprim, const int* am, const in
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->have_basis = true;
   ctx->have_cutoff = ctx->have_screen = false;
+  ++ctx->plan_gen;
   return OQPB_OK;
 }
 
@@ -1011,6 +1050,7 @@ int oqpb_set_cutoff(oqpb_ctx* ctx, double cutoff) {
   ctx->cutoff = cutoff;
   ctx->cut = Cutoffs{cutoff, 1.0e-2 * cutoff, 1.0e-4 * cutoff, 25.0 * std::log(10.0)};  // int2.F90:260-272
   ctx->have_cutoff = true;
+  ++ctx->plan_gen;
   if (ctx->have_screen) {  // re-sort not needed, but the primitive table depends on the cutoffs
     int rc = build_pairtable(ctx, ctx->cut, ctx->run, &ctx->Qmat);
     if (rc) return rc;
@@ -1032,6 +1072,7 @@ int oqpb_set_screening(oqpb_ctx* ctx, const double* schwarz_in) {
   if (rc) return rc;
   CK(ctx->d_dsh.ensure((size_t)ns * ns * sizeof(double)));
   ctx->have_screen = true;
+  ++ctx->plan_gen;
   return OQPB_OK;
 }
 
@@ -1044,6 +1085,7 @@ int oqpb_get_schwarz(oqpb_ctx* ctx, double* out) {
 int oqpb_set_partition(oqpb_ctx* ctx, int rank, int nranks) {
   if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return OQPB_ERR_BAD_ARG;
   ctx->rank = rank;
+  ++ctx->plan_gen;
   ctx->nranks = nranks;
   return OQPB_OK;
 }
