@@ -32,6 +32,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cam", action="store_true", help="range-separated two-pass build (CAM-B3LYP: alpha 0.19, beta 0.46, mu 0.33)")
     ap.add_argument("--nvec", type=int, default=12, help="MRSF workloads (c5): Davidson trial vectors per build (x 7 densities)")
     return ap.parse_args()
 
@@ -91,7 +92,10 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
-def cpu_sample(bs, d_packed, sx, target_s, nthreads=0):
+CAM = {"alpha": 0.19, "beta": 0.46, "mu": 0.33}  # CAM-B3LYP
+
+
+def cpu_sample(bs, d_packed, sx, target_s, nthreads=0, cam=False):
     """Oracle (C++/OpenMP restatement of int2_twoei, the reference's OpenMP CPU path) on a bounded,
     strided sample of the cost-sorted bra shell-pair list of the SAME workload."""
     from oracle.oracle import Oracle, max_threads
@@ -100,14 +104,23 @@ def cpu_sample(bs, d_packed, sx, target_s, nthreads=0):
     npair = bs.nshell * (bs.nshell + 1) // 2
     # probe with a sparse stride, then size the sample for ~target_s seconds
     stride = max(1, npair // 400)
+
+    def build(stride):
+        if cam:
+            _, st = o.fock_cam(d_packed, CAM["alpha"], CAM["beta"], CAM["mu"], nthreads=nthreads, stride=stride, offset=1 % stride)
+            return dict(st, nquartets=st["nquartets_both_passes"])
+        return o.fock(d_packed, sx, 1.0, nthreads=nthreads, stride=stride, offset=1 % stride)[1]
+
+    if cam:
+        o.schwarz_attenuated(CAM["mu"])  # setup, not part of the timed builds
     t = time.perf_counter()
-    _, st = o.fock(d_packed, sx, 1.0, nthreads=nthreads, stride=stride, offset=1 % stride)
+    st = build(stride)
     dt = time.perf_counter() - t
     est_full = dt * stride
     stride2 = max(1, int(round(est_full / target_s)))
     if stride2 < stride:
         t = time.perf_counter()
-        _, st = o.fock(d_packed, sx, 1.0, nthreads=nthreads, stride=stride2, offset=1 % stride2)
+        st = build(stride2)
         dt = time.perf_counter() - t
         stride = stride2
     return {"quartets": st["nquartets"], "seconds": dt, "stride": stride, "cores": max_threads() if nthreads == 0 else nthreads}
@@ -292,7 +305,8 @@ def run_reference(args):
         sampler = cpu_sample
     times, quartets, stride, cores = [], 0, 1, 1
     for it in range(args.warmup + args.steps):
-        r = sampler(bs, dp, sx, args.cpu_seconds if it >= args.warmup else min(args.cpu_seconds, 3.0))
+        kw = {"cam": True} if (args.cam and sampler is cpu_sample) else {}
+        r = sampler(bs, dp, sx, args.cpu_seconds if it >= args.warmup else min(args.cpu_seconds, 3.0), **kw)
         if it >= args.warmup:
             times.append(r["seconds"]); quartets += r["quartets"]; stride = r["stride"]; cores = r["cores"]
     tot = sum(times)
@@ -348,8 +362,14 @@ def main():
     f_dev = torch.zeros_like(d_dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
+    if args.cam:
+        drv.set_screening_cam(CAM["mu"])  # attenuated Schwarz matrix: once per geometry, like set_screening
+
     def step_dev():
-        drv.fock_dev(d_dev.data_ptr(), f_dev.data_ptr(), 1, scale_exchange=sx)
+        if args.cam:
+            drv.fock_cam_dev(d_dev.data_ptr(), f_dev.data_ptr(), 1, CAM["alpha"], CAM["beta"], CAM["mu"])
+        else:
+            drv.fock_dev(d_dev.data_ptr(), f_dev.data_ptr(), 1, scale_exchange=sx)
         if world > 1:
             dist.all_reduce(f_dev)
         drv.fock_post_dev(f_dev.data_ptr(), 1)
@@ -398,7 +418,12 @@ def main():
     ns = C.c_longlong(0)
 
     def step_host():
-        if world == 1:
+        if world == 1 and args.cam:
+            rc = lib().oqpb_fock_cam(drv._h, 0, C.c_void_p(d_pin.data_ptr()), C.c_void_p(f_pin.data_ptr()), 1,
+                                     C.c_double(CAM["alpha"]), C.c_double(CAM["beta"]), C.c_double(CAM["mu"]),
+                                     C.c_double(1.0), C.c_double(0.0), 1, C.byref(ns))
+            assert rc == 0
+        elif world == 1:
             rc = lib().oqpb_fock(drv._h, 0, C.c_void_p(d_pin.data_ptr()), C.c_void_p(f_pin.data_ptr()), 1, C.c_double(sx),
                                  C.c_double(1.0), 1, C.byref(ns))
             assert rc == 0
@@ -438,6 +463,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": W.WORKLOADS.get(args.workload, args.workload), "nshell": bs.nshell, "nbf": bs.nbf,
                        "cutoff": 5e-11, "scale_exchange": sx, "density": "synthetic decaying, seed 7",
+                       "cam": dict(CAM, passes=2) if args.cam else None,
                        "quartets_per_build": nq_step, "fock_builds_per_s": 1e3 / ms_per_step,
                        "l2": "flushed between steps (256 MB fill)", "schwarz_setup_s": t_screen,
                        "parallelism": f"bra shell pairs cyclic over {world} GPU(s), 1 NCCL all-reduce of the packed Fock"},
@@ -453,7 +479,7 @@ def main():
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
-            r = cpu_sample(bs, d, sx, args.cpu_seconds)
+            r = cpu_sample(bs, d, sx, args.cpu_seconds, cam=args.cam)
             line["cpu_baseline"] = {"value": r["quartets"] / r["seconds"], "unit": "quartets/s", "cores": r["cores"], "kind": "port",
                                     "sample": f"every {r['stride']}-th bra shell pair of the cost-sorted list, "
                                               f"{r['quartets']} quartets in {r['seconds']:.1f} s"}

@@ -39,6 +39,12 @@ module oqp_b200_shim
       real(c_double), intent(in) :: d(*); real(c_double), intent(out) :: f(*)
       real(c_double), value :: se, sc; integer(c_long_long), intent(out) :: nskipped
     end function
+    integer(c_int) function oqpb_fock_cam(ctx, urohf, d, f, nfocks, alpha, beta, mu, alpha_coulomb, beta_coulomb, post, &
+                                          nskipped) bind(C, name="oqpb_fock_cam")
+      import; type(c_ptr), value :: ctx; integer(c_int), value :: urohf, nfocks, post
+      real(c_double), intent(in) :: d(*); real(c_double), intent(out) :: f(*)
+      real(c_double), value :: alpha, beta, mu, alpha_coulomb, beta_coulomb; integer(c_long_long), intent(out) :: nskipped
+    end function
     integer(c_int) function oqpb_jk_td(ctx, d2, nvec, flags, se, sc, apb, amb, nskipped) bind(C, name="oqpb_jk_td")
       import; type(c_ptr), value :: ctx; integer(c_int), value :: nvec, flags
       real(c_double), intent(in) :: d2(*); real(c_double), intent(out) :: apb(*), amb(*)
@@ -67,6 +73,7 @@ module oqp_b200_shim
     procedure :: set_screening => shim_set_screening
     procedure :: set_cutoff => shim_set_cutoff
     procedure :: run_fock => shim_run_fock      !< int2_rhf_data_t / int2_urohf_data_t
+    procedure :: run_fock_cam => shim_run_fock_cam  !< same consumers through int2_run_cam (int2.F90:538-584)
     procedure :: run_td => shim_run_td          !< int2_td_data_t
     procedure :: run_mrsf => shim_run_mrsf      !< int2_mrsf_data_t
     procedure :: clean => shim_clean
@@ -128,6 +135,24 @@ contains
     integer(c_long_long) :: ns
     info = oqpb_fock(this%ctx, merge(1_c_int, 0_c_int, urohf), d, f, int(size(d, 2), c_int), scale_exchange, &
                      scale_coulomb, merge(1_c_int, 0_c_int, post), ns)
+    if (info == 0) this%skipped = int(ns)
+  end subroutine
+
+  !> run(consumer, cam=.true., alpha, beta, mu): regular pass + Erf-attenuated pass into the same f
+  subroutine shim_run_fock_cam(this, urohf, d, f, alpha, beta, mu, post, info, alpha_coulomb, beta_coulomb)
+    class(oqpb_int2_t), intent(inout) :: this
+    logical, intent(in) :: urohf, post
+    real(dp), contiguous, intent(in) :: d(:,:)
+    real(dp), contiguous, intent(out) :: f(:,:)
+    real(dp), intent(in) :: alpha, beta, mu
+    integer, intent(out) :: info
+    real(dp), intent(in), optional :: alpha_coulomb, beta_coulomb
+    integer(c_long_long) :: ns
+    real(dp) :: ac, bc
+    ac = 1.0_dp; if (present(alpha_coulomb)) ac = alpha_coulomb
+    bc = 0.0_dp; if (present(beta_coulomb)) bc = beta_coulomb
+    info = oqpb_fock_cam(this%ctx, merge(1_c_int, 0_c_int, urohf), d, f, int(size(d, 2), c_int), alpha, beta, mu, ac, bc, &
+                         merge(1_c_int, 0_c_int, post), ns)
     if (info == 0) this%skipped = int(ns)
   end subroutine
 

@@ -77,6 +77,20 @@ int oqpb_fock(oqpb_ctx* ctx, int urohf, const double* d, double* f, int nfocks, 
 int oqpb_fock_dev(oqpb_ctx* ctx, int urohf, const double* d_dev, double* f_dev, int nfocks,
                   double scale_exchange, double scale_coulomb);
 int oqpb_fock_post_dev(oqpb_ctx* ctx, double* f_dev, int nfocks);
+
+/* Range-separated (CAM) build = int2_compute_t%run(consumer, cam=.true., alpha, beta, mu), i.e. int2_run_cam
+ * (int2.F90:538-584): pass 1 regular integrals with (scale_coulomb, scale_exchange) = (alpha_coulomb, alpha), pass 2
+ * Erf-attenuated integrals erf(mu r)/r (int_rys.F90:179-181, 225-227) with (beta_coulomb, beta), screened with the
+ * attenuated Schwarz matrix (int2.F90:674-685), both into the same Fock matrices.  The legacy seam declines CAM
+ * (scf_addons.F90:1141); fock_jk passes alpha_coulomb = 1, beta_coulomb = 0 (scf_addons.F90:1167-1173).
+ * oqpb_set_screening_cam computes (or takes) the attenuated Schwarz matrix once per geometry and mu; the fock entries
+ * call it themselves when the cached mu differs.  nskipped = the second pass's count, as the reference leaves it.   */
+int oqpb_set_screening_cam(oqpb_ctx* ctx, double mu, const double* schwarz_att_in /* nshell*nshell or NULL */);
+int oqpb_get_schwarz_cam(oqpb_ctx* ctx, double* out /* nshell*nshell */);
+int oqpb_fock_cam(oqpb_ctx* ctx, int urohf, const double* d, double* f, int nfocks, double alpha, double beta,
+                  double mu, double alpha_coulomb, double beta_coulomb, int post, long long* nskipped);
+int oqpb_fock_cam_dev(oqpb_ctx* ctx, int urohf, const double* d_dev, double* f_dev, int nfocks, double alpha,
+                      double beta, double mu, double alpha_coulomb, double beta_coulomb);
 int oqpb_synchronize(oqpb_ctx* ctx);
 void* oqpb_stream(oqpb_ctx* ctx); /* cudaStream_t the ctx launches on */
 /* launch on the caller's stream instead (e.g. the stream the caller's NCCL communicator is ordered on) */

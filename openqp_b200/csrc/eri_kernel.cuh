@@ -95,6 +95,7 @@ struct EriArgs {
   int rys_xmax;
   double herm_r[7], herm_w[7];
   double prim_cutoff;  // pair_cutoff^2 (int_rys.F90:74,232)
+  double mu2inv;       // 1/mu^2 for Erf-attenuated integrals (CAM second pass, int_rys.F90:179-181, 225-227); 0 = regular
   double cutoff;       // element cutoff (int2.F90:1806-1812)
   int mode;
   int nbf;
@@ -1113,7 +1114,7 @@ eri_kernel(const EriArgs A) {
           const double* pq = A.prim + (size_t)(qi.koff + j) * PRIM_STRIDE;
           const double z = __ldg(pp + 3), e = __ldg(pq + 3);
           const double pf = __ldg(pp + 4) * __ldg(pq + 4);
-          if (!(pf * pf < A.prim_cutoff * (z + e))) {
+          if (!(pf * pf < A.prim_cutoff * (z + e + z * e * A.mu2inv))) {
             int pos = atomicAdd(&qi.lcount, 1);
             plist[pos] = (unsigned short)(j * 128 + i);
           }
@@ -1134,7 +1135,7 @@ eri_kernel(const EriArgs A) {
         Px = __ldg(pp); Py = __ldg(pp + 1); Pz = __ldg(pp + 2); zeta = __ldg(pp + 3); Kp = __ldg(pp + 4); zinv = __ldg(pp + 5);
         Qx = __ldg(pq); Qy = __ldg(pq + 1); Qz = __ldg(pq + 2); eta = __ldg(pq + 3); Kq = __ldg(pq + 4); einv = __ldg(pq + 5);
       }
-      const double ab = zeta + eta;
+      const double ab = zeta + eta + zeta * eta * A.mu2inv;
       const double pfac = Kp * Kq;
       const bool keep = act;
       const double abinv = 1.0 / ab;
@@ -1516,7 +1517,7 @@ eri_small_kernel(const EriArgs A) {
         const double zeta = p23.y, zinv = p45.y;
         const double pfac = p45.x * db;
         if (pfac * pfac < thr) break;
-        const double ab = zeta + eta;
+        const double ab = zeta + eta + zeta * eta * A.mu2inv;  // 2nd term: attenuated integrals, int_rys.F90:225-227
         if (pfac * pfac < A.prim_cutoff * ab) continue;  // int_rys.F90:229-232
         if constexpr (!PIPE) p01 = __ldg(pp0 + 3 * kp);
         const double Px = p01.x, Py = p01.y, Pz = p23.x;
@@ -1825,7 +1826,8 @@ eri_group_kernel(const EriArgs A) {
           const double* pp = A.prim + (size_t)(qi.boff + i) * PRIM_STRIDE;
           const double* pq = A.prim + (size_t)(qi.koff + j) * PRIM_STRIDE;
           const double pf = __ldg(pp + 4) * __ldg(pq + 4);
-          if (!(pf * pf < A.prim_cutoff * (__ldg(pp + 3) + __ldg(pq + 3)))) {
+          const double zz = __ldg(pp + 3), ee = __ldg(pq + 3);
+          if (!(pf * pf < A.prim_cutoff * (zz + ee + zz * ee * A.mu2inv))) {
             int pos = atomicAdd(&qi.lcount, 1);
             plist[pos] = (unsigned short)(j * 128 + i);
           }
@@ -1847,7 +1849,7 @@ eri_group_kernel(const EriArgs A) {
         const double PQx = Px - Qx, PQy = Py - Qy, PQz = Pz - Qz;
         // ---- B1: lane 0 of the group prepares the primitive scalars, 2R lanes evaluate roots and weights
         if (keep) {
-          const double abinv = 1.0 / (zeta + eta);
+          const double abinv = 1.0 / (zeta + eta + zeta * eta * A.mu2inv);
           const double rho = zeta * eta * abinv;
           const double X = rho * (PQx * PQx + PQy * PQy + PQz * PQz);
           if (t == 0) { rw[2 * R] = abinv; rw[2 * R + 1] = Kp * Kq * sqrt(abinv); }

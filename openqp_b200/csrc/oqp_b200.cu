@@ -90,6 +90,10 @@ struct PairTable {
   int cls_off[NL + 1] = {0};  // offsets of the NL pair lists (class-major, bucket-minor)
   DevBuf d_ent, d_prim, d_Q, d_canon;
   long nprim = 0;
+  // CAM second pass (int2.F90:674-685): Schwarz bounds of the Erf-attenuated integrals for the same entry order
+  std::vector<double> Qatt, Qsufatt;
+  DevBuf d_Qatt;
+  double att_mu = 0.0;
 };
 
 // FLOP model of SURVEY.md 8(d-1) (restates int_rys.F90:406, 471-713)
@@ -151,6 +155,7 @@ struct oqpb_ctx {
   Cutoffs cut{};
   PairTable run;
   std::vector<double> Qmat;  // nshell x nshell (host)
+  std::vector<double> Qmat_att;  // same for the attenuated integrals (CAM)
   DevBuf d_Qmat, d_dsh, d_maxden, d_ok, d_d4, d_rowsbuf;
   // work
   static constexpr int NSTREAM = 8;  // launch lanes (nlanes of them used): chunk c runs on lane c % NSTREAM (own task buffer) so that the
@@ -173,7 +178,7 @@ struct oqpb_ctx {
   unsigned* h_counts = nullptr;  // pinned
   size_t h_counts_cap = 0;
   double fp64_peak = 0;
-  BuildPlan plan;
+  BuildPlan plan[2];  // [0] regular, [1] attenuated pass
   long plan_gen = 0;  // bumped by set_basis / set_cutoff / set_screening / set_partition
 };
 
@@ -488,8 +493,8 @@ int upload(oqpb_ctx* ctx, DevBuf& b, const std::vector<T>& v) {
 }
 
 int free_pairtable(PairTable& t) {
-  t.d_ent.release(); t.d_prim.release(); t.d_Q.release(); t.d_canon.release();
-  t.ent.clear(); t.canon.clear(); t.Q.clear();
+  t.d_ent.release(); t.d_prim.release(); t.d_Q.release(); t.d_canon.release(); t.d_Qatt.release();
+  t.ent.clear(); t.canon.clear(); t.Q.clear(); t.Qatt.clear(); t.Qsufatt.clear(); t.att_mu = 0.0;
   return 0;
 }
 
@@ -561,6 +566,7 @@ int build_pairtable(oqpb_ctx* ctx, const Cutoffs& c, PairTable& T, const std::ve
     }
   }
   T.ent.clear(); T.canon.clear(); T.Q.clear();
+  T.Qatt.clear(); T.Qsufatt.clear(); T.att_mu = 0.0;
   long poff = 0;
   for (int pc = 0; pc < NL; ++pc) {
     T.cls_off[pc] = (int)T.ent.size();
@@ -619,6 +625,7 @@ void fill_common_args(oqpb_ctx* ctx, const PairTable& T, int la_, int lb_, EriAr
   A.rys_xmax = RYS_XMAX_H[R - 1];
   for (int k = 0; k < 7; ++k) { A.herm_r[k] = RYS_HERM_R_H[R - 1][k]; A.herm_w[k] = RYS_HERM_W_H[R - 1][k]; }
   A.nbf = ctx->nbf;
+  A.mu2inv = 0.0;
 }
 
 int ensure_counts(oqpb_ctx* ctx, size_t n) {
@@ -632,7 +639,8 @@ int ensure_counts(oqpb_ctx* ctx, size_t n) {
 }
 
 // Schwarz matrix on the device: ints_exchange, int2.F90:1582-1737
-int schwarz(oqpb_ctx* ctx) {
+// mu > 0: bounds of the Erf-attenuated integrals (ints_exchange(..., mu2), int2.F90:678); result in Qout (nshell^2)
+int schwarz(oqpb_ctx* ctx, double mu, std::vector<double>& Qout) {
   Cutoffs c{1.0e-15, 1.0e-17, 1.0e-17, 50.0};  // int2.F90:1600-1604
   PairTable T;
   int rc = build_pairtable(ctx, c, T, nullptr);
@@ -665,6 +673,7 @@ int schwarz(oqpb_ctx* ctx) {
     A.counter = d_cnt.as<unsigned>() + 2 * pc + 1;
     A.prim_cutoff = c.pair * c.pair;
     A.cutoff = 0.0;
+    A.mu2inv = mu > 0 ? 1.0 / (mu * mu) : 0.0;
     A.mode = MODE_SCHWARZ;
     A.qout = d_q.as<double>() + T.cls_off[pc];
     const ClassEntry& ce = tab[quartet_class(pc_of(pc), pc_of(pc))];
@@ -675,10 +684,10 @@ int schwarz(oqpb_ctx* ctx) {
   std::vector<double> q(nent);
   CK(cudaMemcpyAsync(q.data(), d_q.p, nent * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  ctx->Qmat.assign((size_t)ns * ns, 0.0);
+  Qout.assign((size_t)ns * ns, 0.0);
   for (size_t e = 0; e < nent; ++e) {
     int i = T.ent[e].sa, j = T.ent[e].sb;
-    ctx->Qmat[(size_t)i * ns + j] = ctx->Qmat[(size_t)j * ns + i] = q[e];
+    Qout[(size_t)i * ns + j] = Qout[(size_t)j * ns + i] = q[e];
   }
   free_pairtable(T);
   d_q.release(); d_tasks.release(); d_cnt.release();
@@ -698,6 +707,7 @@ struct BuildSpec {
   int gen_nm = 0, gen_ncoul = 0, gen_nvec = 0;
   double cj = 0, ck = 0;
   double digest_flops_per_int = 0;
+  bool attenuated = false;  // CAM second pass: attenuated integrals + attenuated Schwarz bounds (ctx->run.att_mu)
 };
 
 // int2_twoei (int2.F90:589-923): screening data must already be in d_dsh / d_maxden.
@@ -706,10 +716,17 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   const int ns = ctx->nshell;
   const long nent = (long)T.ent.size();
   const double cutoff = ctx->cut.integral;
+  if (S.attenuated && !(T.att_mu > 0 && T.Qatt.size() == T.ent.size())) {
+    ctx->err = "attenuated pass without oqpb_set_screening_cam";
+    return OQPB_ERR_STATE;
+  }
+  const std::vector<double>& hQ = S.attenuated ? T.Qatt : T.Q;
+  const std::vector<double>& hQsuf = S.attenuated ? T.Qsufatt : T.Qsuf;
+  const double* dQ = S.attenuated ? T.d_Qatt.as<double>() : T.d_Q.as<double>();
   CK(ctx->d_ok.ensure(nent * sizeof(int)));
   CK(ctx->d_d4.ensure(nent * sizeof(double)));
   k_entry_screen<<<(unsigned)((nent + 255) / 256), 256, 0, ctx->stream>>>(
-      nent, T.d_ent.as<PairEntry>(), T.d_Q.as<double>(), ctx->d_dsh.as<double>(), ns,
+      nent, T.d_ent.as<PairEntry>(), dQ, ctx->d_dsh.as<double>(), ns,
       ctx->d_maxden.as<unsigned long long>(), cutoff, ctx->d_ok.as<int>(), ctx->d_d4.as<double>());
   CK(cudaGetLastError());
   static const bool timing = getenv("OQPB_TIMING") != nullptr;
@@ -727,7 +744,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   const int nr = ctx->nranks, rk = ctx->rank;
   double bound4p = bound4;
   if (bound4 > 0) { int e; std::frexp(bound4, &e); bound4p = std::ldexp(1.0, e); }  // next power of two >= bound4
-  BuildPlan& P = ctx->plan;
+  BuildPlan& P = ctx->plan[S.attenuated ? 1 : 0];
   DevBuf& d_km = ctx->d_rowsbuf;
   int rc;
   double t_planned = tnow(), t_uploaded = t_planned;
@@ -742,10 +759,10 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
       for (int pcb = 0; pcb <= pca; ++pcb) {
         int nb = T.cls_off[pcb + 1] - T.cls_off[pcb];
         if (nb == 0) continue;
-        const double* Qa = T.Q.data() + T.cls_off[pca];
+        const double* Qa = hQ.data() + T.cls_off[pca];
         std::vector<int> km(na, 0);
         // kets at or beyond km[p] cannot survive: suffix maxima of the ket list's bounds are monotone
-        const double* Qs = T.Qsuf.data() + T.cls_off[pcb];
+        const double* Qs = hQsuf.data() + T.cls_off[pcb];
 #pragma omp parallel for schedule(static) if (na > 4096)
         for (int p = rk; p < na; p += nr) {  // this rank's bras only
           int lo = 0, hi = nb;  // first k with Qa[p] * Qs[k] * bound4p < cutoff
@@ -835,8 +852,8 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     // first bra of this rank at or after p0
     int pstart = ch.p0 + ((rk - ch.p0 % nr) % nr + nr) % nr;
     k_enum<<<nbra, ENUM_NT, use_smem ? smem_rows : 0, cs>>>(
-        T.d_ent.as<PairEntry>() + offa, T.d_ent.as<PairEntry>() + offb, T.d_Q.as<double>() + offa,
-        T.d_Q.as<double>() + offb, ctx->d_d4.as<double>() + offa, ctx->d_d4.as<double>() + offb,
+        T.d_ent.as<PairEntry>() + offa, T.d_ent.as<PairEntry>() + offb, dQ + offa,
+        dQ + offb, ctx->d_d4.as<double>() + offa, ctx->d_d4.as<double>() + offb,
         ctx->d_ok.as<int>() + offa, ctx->d_ok.as<int>() + offb, T.d_canon.as<int>() + offa,
         T.d_canon.as<int>() + offb, d_km.as<int>() + km_off[ci], pstart, ch.p1, nr, ch.pca == ch.pcb,
         ctx->d_dsh.as<double>(), ns, cutoff, d_tasks, d_cnt + 2 * c, (unsigned)ctx->task_cap, use_smem);
@@ -848,6 +865,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     A.counter = d_cnt + 2 * c + 1;
     A.prim_cutoff = ctx->cut.pair * ctx->cut.pair;
     A.cutoff = cutoff;
+    A.mu2inv = S.attenuated ? 1.0 / (T.att_mu * T.att_mu) : 0.0;
     A.stat = ctx->d_stats.as<unsigned long long>() + 2 * c;
     A.mode = S.mode;
     A.nmat = S.nmat;
@@ -1065,7 +1083,7 @@ int oqpb_set_screening(oqpb_ctx* ctx, const double* schwarz_in) {
   if (schwarz_in) {
     ctx->Qmat.assign(schwarz_in, schwarz_in + (size_t)ns * ns);
   } else {
-    int rc = schwarz(ctx);
+    int rc = schwarz(ctx, 0.0, ctx->Qmat);
     if (rc) return rc;
   }
   int rc = build_pairtable(ctx, ctx->cut, ctx->run, &ctx->Qmat);
@@ -1073,6 +1091,37 @@ int oqpb_set_screening(oqpb_ctx* ctx, const double* schwarz_in) {
   CK(ctx->d_dsh.ensure((size_t)ns * ns * sizeof(double)));
   ctx->have_screen = true;
   ++ctx->plan_gen;
+  return OQPB_OK;
+}
+
+// Schwarz bounds of the Erf-attenuated integrals erf(mu r)/r for the CAM second pass (int2.F90:674-685); the pair
+// lists keep the order of the regular bounds, the enumeration's cut-off uses the suffix maxima of the new bounds.
+int oqpb_set_screening_cam(oqpb_ctx* ctx, double mu, const double* schwarz_att_in) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!(mu > 0)) return OQPB_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  const int ns = ctx->nshell;
+  PairTable& T = ctx->run;
+  if (T.att_mu == mu && T.Qatt.size() == T.ent.size() && !schwarz_att_in) return OQPB_OK;
+  std::vector<double> Qm;
+  if (schwarz_att_in) Qm.assign(schwarz_att_in, schwarz_att_in + (size_t)ns * ns);
+  else if ((rc = schwarz(ctx, mu, Qm))) return rc;
+  ctx->Qmat_att = Qm;
+  T.Qatt.resize(T.ent.size());
+  for (size_t e = 0; e < T.ent.size(); ++e) T.Qatt[e] = Qm[(size_t)T.ent[e].sa * ns + T.ent[e].sb];
+  T.Qsufatt = T.Qatt;
+  for (int pc = 0; pc < NL; ++pc)
+    for (int k = T.cls_off[pc + 1] - 2; k >= T.cls_off[pc]; --k) T.Qsufatt[k] = std::max(T.Qsufatt[k], T.Qsufatt[k + 1]);
+  if ((rc = upload(ctx, T.d_Qatt, T.Qatt))) return rc;
+  T.att_mu = mu;
+  ctx->plan[1].valid = false;
+  return OQPB_OK;
+}
+
+int oqpb_get_schwarz_cam(oqpb_ctx* ctx, double* out) {
+  if (!ctx || ctx->Qmat_att.empty()) return OQPB_ERR_STATE;
+  memcpy(out, ctx->Qmat_att.data(), ctx->Qmat_att.size() * sizeof(double));
   return OQPB_OK;
 }
 
@@ -1090,7 +1139,10 @@ int oqpb_set_partition(oqpb_ctx* ctx, int rank, int nranks) {
   return OQPB_OK;
 }
 
-int oqpb_fock_dev(oqpb_ctx* ctx, int urohf, const double* d_dev, double* f_dev, int nfocks, double se, double sc) {
+// npass = 1: regular build.  npass = 2: int2_run_cam (int2.F90:538-584): pass 1 regular integrals with (sc[0], se[0]),
+// pass 2 Erf-attenuated integrals with (sc[1], se[1]), both accumulated into the same Fock matrices.
+static int fock_core(oqpb_ctx* ctx, int urohf, const double* d_dev, double* f_dev, int nfocks, int npass, const double* se,
+                     const double* sc) {
   int rc = check_ready(ctx);
   if (rc) return rc;
   cudaSetDevice(ctx->device);
@@ -1113,18 +1165,40 @@ int oqpb_fock_dev(oqpb_ctx* ctx, int urohf, const double* d_dev, double* f_dev, 
   if (urohf) k_add<<<(unsigned)((n2 + 255) / 256), 256, 0, ctx->stream>>>(Dsq, Dsq + n2, Dsq + 2 * n2, n2);
   CK(cudaGetLastError());
   CK(cudaMemsetAsync(f_dev, 0, (size_t)nfocks * ntri * sizeof(double), ctx->stream));
-  BuildSpec S;
-  S.mode = MODE_SYM;
-  S.nmat = nfocks;
-  for (int m = 0; m < nfocks; ++m) {
-    S.DJ[m] = urohf ? Dsq + 2 * n2 : Dsq + (size_t)m * n2;
-    S.DK[m] = Dsq + (size_t)m * n2;
-    S.F[m] = f_dev + (size_t)m * ntri;
+  double kernel_ms = 0, flops = 0;
+  long long surv = 0, launches = 0;
+  for (int pass = 0; pass < npass; ++pass) {
+    BuildSpec S;
+    S.mode = MODE_SYM;
+    S.nmat = nfocks;
+    for (int m = 0; m < nfocks; ++m) {
+      S.DJ[m] = urohf ? Dsq + 2 * n2 : Dsq + (size_t)m * n2;
+      S.DK[m] = Dsq + (size_t)m * n2;
+      S.F[m] = f_dev + (size_t)m * ntri;
+    }
+    S.cj = sc[pass];                          // 4*sc applied in the kernel (xval4, int2.F90:1423 / 1499)
+    S.ck = urohf ? 2.0 * se[pass] : se[pass];  // xval1 (int2.F90:1422) / xval2 (int2.F90:1498)
+    S.digest_flops_per_int = urohf ? 26.0 : 14.0 * nfocks;
+    S.attenuated = pass == 1;
+    if ((rc = run_build(ctx, S))) return rc;
+    kernel_ms += ctx->st_kernel_ms; flops += ctx->st_flops; surv += ctx->st_survivors; launches += ctx->st_launches;
   }
-  S.cj = sc;                    // 4*sc applied in the kernel (xval4, int2.F90:1423 / 1499)
-  S.ck = urohf ? 2.0 * se : se;  // xval1 (int2.F90:1422) / xval2 (int2.F90:1498)
-  S.digest_flops_per_int = urohf ? 26.0 : 14.0 * nfocks;
-  return run_build(ctx, S);
+  // `skipped` stays what the last run_generic left (the reference overwrites it per pass); the rest is summed
+  ctx->st_kernel_ms = kernel_ms; ctx->st_flops = flops; ctx->st_survivors = surv; ctx->st_launches = launches;
+  return OQPB_OK;
+}
+
+int oqpb_fock_dev(oqpb_ctx* ctx, int urohf, const double* d_dev, double* f_dev, int nfocks, double se, double sc) {
+  return fock_core(ctx, urohf, d_dev, f_dev, nfocks, 1, &se, &sc);
+}
+
+int oqpb_fock_cam_dev(oqpb_ctx* ctx, int urohf, const double* d_dev, double* f_dev, int nfocks, double alpha, double beta,
+                      double mu, double alpha_coulomb, double beta_coulomb) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if ((rc = oqpb_set_screening_cam(ctx, mu, nullptr))) return rc;  // no-op when the bounds for this mu are cached
+  const double se[2] = {alpha, beta}, sc[2] = {alpha_coulomb, beta_coulomb};
+  return fock_core(ctx, urohf, d_dev, f_dev, nfocks, 2, se, sc);
 }
 
 int oqpb_fock_post_dev(oqpb_ctx* ctx, double* f_dev, int nfocks) {
@@ -1164,6 +1238,26 @@ int oqpb_fock(oqpb_ctx* ctx, int urohf, const double* d, double* f, int nfocks, 
   CK(ctx->d_F.ensure(bytes));
   CK(cudaMemcpyAsync(ctx->d_Din.p, d, bytes, cudaMemcpyHostToDevice, ctx->stream));
   rc = oqpb_fock_dev(ctx, urohf, ctx->d_Din.as<double>(), ctx->d_F.as<double>(), nfocks, se, sc);
+  if (rc) return rc;
+  if (post) { rc = oqpb_fock_post_dev(ctx, ctx->d_F.as<double>(), nfocks); if (rc) return rc; }
+  CK(cudaMemcpyAsync(f, ctx->d_F.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (nskipped) *nskipped = ctx->st_skipped;
+  return OQPB_OK;
+}
+
+int oqpb_fock_cam(oqpb_ctx* ctx, int urohf, const double* d, double* f, int nfocks, double alpha, double beta, double mu,
+                  double alpha_coulomb, double beta_coulomb, int post, long long* nskipped) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  cudaSetDevice(ctx->device);
+  const long ntri = (long)ctx->nbf * (ctx->nbf + 1) / 2;
+  size_t bytes = (size_t)nfocks * ntri * sizeof(double);
+  CK(ctx->d_Din.ensure(bytes));
+  CK(ctx->d_F.ensure(bytes));
+  CK(cudaMemcpyAsync(ctx->d_Din.p, d, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  rc = oqpb_fock_cam_dev(ctx, urohf, ctx->d_Din.as<double>(), ctx->d_F.as<double>(), nfocks, alpha, beta, mu, alpha_coulomb,
+                         beta_coulomb);
   if (rc) return rc;
   if (post) { rc = oqpb_fock_post_dev(ctx, ctx->d_F.as<double>(), nfocks); if (rc) return rc; }
   CK(cudaMemcpyAsync(f, ctx->d_F.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));

@@ -112,9 +112,28 @@ class Int2Compute:
     def set_partition(self, rank: int, nranks: int):
         self._check(lib().oqpb_set_partition(self._h, C.c_int(rank), C.c_int(nranks)), "oqpb_set_partition")
 
-    # -- int2_compute_t%run (int2.F90:500, 589) ---------------------------------------------------
-    def run(self, consumer):
-        consumer._run(self)
+    def set_screening_cam(self, mu: float, schwarz_att=None):
+        """Schwarz matrix of the Erf-attenuated integrals for the CAM second pass (int2.F90:674-685)"""
+        if schwarz_att is None:
+            self._check(lib().oqpb_set_screening_cam(self._h, C.c_double(mu), None), "oqpb_set_screening_cam")
+        else:
+            q = np.ascontiguousarray(schwarz_att, dtype=np.float64)
+            self._check(lib().oqpb_set_screening_cam(self._h, C.c_double(mu), _dp(q)), "oqpb_set_screening_cam")
+        ns = self.basis.nshell
+        q = np.zeros((ns, ns))
+        self._check(lib().oqpb_get_schwarz_cam(self._h, _dp(q)), "oqpb_get_schwarz_cam")
+        return q
+
+    # -- int2_compute_t%run (int2.F90:500-536, 589) -----------------------------------------------
+    def run(self, consumer, cam=False, alpha=1.0, beta=0.0, mu=0.0, alpha_coulomb=1.0, beta_coulomb=0.0):
+        """run(consumer): one pass with the consumer's scale factors.  run(consumer, cam=True, alpha, beta, mu): the
+        range-separated two-pass build int2_run_cam (int2.F90:538-584); SCF consumers only (RHF / UROHF)."""
+        if cam:
+            if not hasattr(consumer, "_run_cam"):
+                raise Int2Error("cam=True is implemented for Int2RhfData / Int2UrohfData")
+            consumer._run_cam(self, alpha, beta, mu, alpha_coulomb, beta_coulomb)
+        else:
+            consumer._run(self)
         self.skipped = consumer.skipped
         return consumer
 
@@ -134,6 +153,12 @@ class Int2Compute:
         self._check(lib().oqpb_fock_dev(self._h, C.c_int(1 if urohf else 0), C.c_void_p(d_ptr), C.c_void_p(f_ptr),
                                         C.c_int(nfocks), C.c_double(scale_exchange), C.c_double(scale_coulomb)),
                     "oqpb_fock_dev")
+
+    def fock_cam_dev(self, d_ptr: int, f_ptr: int, nfocks: int, alpha, beta, mu, urohf=False, alpha_coulomb=1.0, beta_coulomb=0.0):
+        """int2_run_cam (int2.F90:538-584) with device-resident packed d / f (raw accumulator; fock_post_dev scales)"""
+        self._check(lib().oqpb_fock_cam_dev(self._h, C.c_int(1 if urohf else 0), C.c_void_p(d_ptr), C.c_void_p(f_ptr),
+                                            C.c_int(nfocks), C.c_double(alpha), C.c_double(beta), C.c_double(mu),
+                                            C.c_double(alpha_coulomb), C.c_double(beta_coulomb)), "oqpb_fock_cam_dev")
 
     def mrsf_dev(self, d3_ptr: int, f3_ptr: int, nvec: int, ncomp: int = 7, scale_exchange=1.0, scale_coulomb=1.0):
         """int2_mrsf_data_t with device-resident d3 / f3 (layout d3(v, c, mu, nu), v fastest)"""
@@ -229,6 +254,18 @@ class Int2RhfData:
         drv._check(lib().oqpb_fock(drv._h, C.c_int(1 if self.urohf else 0), _dp(self.d), _dp(self.f), C.c_int(nf),
                                    C.c_double(self.scale_exchange), C.c_double(self.scale_coulomb),
                                    C.c_int(1 if self.post else 0), C.byref(ns)), "oqpb_fock")
+        self.skipped = int(ns.value)
+
+
+    def _run_cam(self, drv: Int2Compute, alpha, beta, mu, alpha_coulomb, beta_coulomb):
+        nf, ntri = self.d.shape
+        assert ntri == drv.basis.ntri
+        self.f = np.zeros_like(self.d)
+        ns = C.c_longlong(0)
+        drv._check(lib().oqpb_fock_cam(drv._h, C.c_int(1 if self.urohf else 0), _dp(self.d), _dp(self.f), C.c_int(nf),
+                                       C.c_double(alpha), C.c_double(beta), C.c_double(mu), C.c_double(alpha_coulomb),
+                                       C.c_double(beta_coulomb), C.c_int(1 if self.post else 0), C.byref(ns)),
+                   "oqpb_fock_cam")
         self.skipped = int(ns.value)
 
 

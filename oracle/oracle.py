@@ -110,6 +110,39 @@ class Oracle:
             lib().orc_fock_post(C.c_int(self.basis.nbf), C.c_int(nf), _p(f))
         return f, st
 
+    def set_attenuation(self, mu: float):
+        """switch to Erf-attenuated integrals erf(mu r)/r and the attenuated Schwarz matrix (mu > 0) or back (mu = 0)"""
+        lib().orc_set_attenuation(self.h, C.c_double(mu))
+
+    def active_schwarz(self):
+        ns = self.basis.nshell
+        q = np.zeros((ns, ns))
+        lib().orc_get_schwarz(self.h, _p(q))
+        return q
+
+    def schwarz_attenuated(self, mu: float):
+        """Schwarz matrix of the Erf-attenuated integrals (ints_exchange with mu2, int2.F90:674-681)"""
+        self.set_attenuation(mu)
+        q = self.active_schwarz()
+        self.set_attenuation(0.0)
+        return q
+
+    def fock_cam(self, d_packed, alpha, beta, mu, alpha_coulomb=1.0, beta_coulomb=0.0, urohf=False, nthreads=0,
+                 stride=1, offset=0):
+        """int2_run_cam (int2.F90:538-584): pass 1 regular integrals with (scale_coulomb, scale_exchange) =
+        (alpha_coulomb, alpha); pass 2 attenuated integrals with (beta_coulomb, beta); both into the same Fock, then the
+        fock_jk post-scaling.  Returns (f, stats of pass 2) -- `skipped` is what the second run_generic leaves."""
+        f1, st1 = self.fock(d_packed, alpha, alpha_coulomb, urohf=urohf, nthreads=nthreads, post=False, stride=stride, offset=offset)
+        self.set_attenuation(mu)
+        try:
+            f2, st = self.fock(d_packed, beta, beta_coulomb, urohf=urohf, nthreads=nthreads, post=False, stride=stride, offset=offset)
+        finally:
+            self.set_attenuation(0.0)
+        f = np.ascontiguousarray(f1 + f2)
+        lib().orc_fock_post(C.c_int(self.basis.nbf), C.c_int(f.shape[0]), _p(f))
+        st = dict(st, nquartets_both_passes=st1["nquartets"] + st["nquartets"])
+        return f, st
+
     def td(self, d2, scale_exchange=1.0, scale_coulomb=1.0, int_apb=True, int_amb=False, tamm_dancoff=False,
            tamm_dancoff_coulomb=False, nthreads=0, post=True):
         """int2_td_data_t (tdhf_lib.F90:11-31): d2[v] = P_v as numpy (nvec, nbf, nbf) with P_v[mu,nu];

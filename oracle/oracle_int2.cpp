@@ -307,6 +307,7 @@ struct Eri {
   std::vector<double> ints, gijkl, gnkl, gnm, b00, b01, b10, c00, d00, abv, PQ, PB, QD, dij, dkl, rw;
   int idx[3][MXCART][4];
   double quartet_cutoff;
+  double mu2_1 = 0.0;  // 1/mu^2 for Erf-attenuated integrals (int_rys.F90:179-181), 0 = regular
   void init(int maxang, const Cutoffs &c) {  // int_rys.F90:62-99
     quartet_cutoff = c.pair2;  // :74
     int mxrys = (4 * maxang + 2) / 2, mxcart = maxang + 1, mxbra = 2 * mxcart - 1;
@@ -513,7 +514,7 @@ bool rys_compute(Eri &g, const Basis &b, const Pairs &pp) {
     for (int ijg = 0; ijg < npp_p; ijg++) {
       int p = ppid_p + ijg;
       double da = pp.k[p] * pp.ginv[p], aa = pp.g[p];
-      double ab = (aa + bb);  // + aa*bb/mu^2 for attenuated integrals (not restated: CAM is SURVEY 8f "next")
+      double ab = (aa + bb) + aa * bb * g.mu2_1;  // 2nd term: Erf-attenuated integrals, int_rys.F90:225-227
       double pfac = da * db, test = pfac * pfac;
       if (test < g.quartet_cutoff * ab) continue;
       double aandb1 = 1.0 / ab, rho = aa * bb * aandb1;
@@ -553,10 +554,13 @@ struct Oracle {
   Pairs pp;
   std::vector<double> schwarz;  // nshell x nshell
   double cutoff = 5e-11;
+  // range-separated (CAM) second pass, int2.F90:538-584, 674-685: attenuated Schwarz matrix and mu of the active pass
+  std::vector<double> schwarz_regular, schwarz_att;
+  double mu = 0.0;  // > 0: attenuated integrals erf(mu r)/r
 };
 
 // ints_exchange, int2.F90:1582-1737 (Rys branch)
-void ints_exchange(Oracle &o) {
+void ints_exchange(Oracle &o, double mu = 0.0) {
   Cutoffs c;
   c.set(1.0e-15, 1.0e-17, 1.0e-17, 50.0);  // :1600-1604
   Pairs pp;
@@ -568,6 +572,7 @@ void ints_exchange(Oracle &o) {
   {
     Eri g;
     g.init(lmax, c);
+    g.mu2_1 = mu > 0 ? 1.0 / (mu * mu) : 0.0;  // ints_exchange(..., mu2), int2.F90:678
 #pragma omp for schedule(dynamic, 4)
     for (int ish = 0; ish < ns; ish++)
       for (int jsh = 0; jsh <= ish; jsh++) {
@@ -859,6 +864,7 @@ void twoei(Oracle &o, Consumer &c, double *f, double *f2, size_t fsize, size_t f
     }
     Eri g;
     g.init(lmax, o.cut);
+    g.mu2_1 = o.mu > 0 ? 1.0 / (o.mu * o.mu) : 0.0;  // mu2 = this%mu**2 when attenuated (int2.F90:1098-1101)
     Buf buf;
     auto flush = [&]() { update(c, buf, F, F2, collect_ids, collect_vals); };
 #pragma omp for schedule(dynamic, 1)
@@ -1035,6 +1041,30 @@ void orc_set_schwarz(void *h, const double *in) {
   o->schwarz.assign(in, in + (size_t)o->b.nshell * o->b.nshell);
 }
 
+// int2_run_cam pass switch (int2.F90:538-584): mu > 0 selects attenuated integrals and the attenuated Schwarz matrix
+// (computed on first use, :674-681); mu = 0 goes back to the regular pass.
+void orc_set_attenuation(void *h, double mu) {
+  Oracle *o = (Oracle *)h;
+  if (o->schwarz_regular.empty() && o->mu == 0.0) o->schwarz_regular = o->schwarz;
+  if (mu > 0) {
+    if (o->schwarz_att.empty() || o->mu != mu) {
+      if (o->mu == 0.0) o->schwarz_regular = o->schwarz;
+      ints_exchange(*o, mu);  // fills o->schwarz
+      o->schwarz_att = o->schwarz;
+    }
+    o->schwarz = o->schwarz_att;
+    o->mu = mu;
+  } else {
+    if (o->mu > 0) o->schwarz = o->schwarz_regular;
+    o->mu = 0.0;
+  }
+}
+
+void orc_get_schwarz(void *h, double *out) {  // the matrix of the active pass
+  Oracle *o = (Oracle *)h;
+  std::memcpy(out, o->schwarz.data(), o->schwarz.size() * sizeof(double));
+}
+
 void orc_rys(int nroots, double x, double *u, double *w) { rys_general(x, nroots, u, w); }
 
 // one shell quartet (0-based shells); out(l,k,j,i) in ORIGINAL shell order i,j,k,l (l fastest), nout[4]
@@ -1042,6 +1072,7 @@ int orc_eri_block(void *h, int i, int j, int k, int l, double *out, int *nout) {
   Oracle *o = (Oracle *)h;
   Eri g;
   g.init(*std::max_element(o->b.am.begin(), o->b.am.end()), o->cut);
+  g.mu2_1 = o->mu > 0 ? 1.0 / (o->mu * o->mu) : 0.0;
   int ids[4] = {i, j, k, l};
   set_ids(g, o->b, ids);
   bool zero = rys_compute(g, o->b, o->pp);

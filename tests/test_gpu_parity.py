@@ -330,3 +330,33 @@ def test_full_size_properties_w32_and_mrsf(drv):
     assert np.abs(f3[0, 3] - f3[0, 0]).max() < 1e-10
     assert np.abs(f3[0, 6] - 2 * unpack(frk, bs5.nbf)).max() < 2e-9
     assert np.isfinite(fk).all()
+
+
+def test_cam_two_pass_build(oracle_mod, drv):
+    """Range-separated build int2_run_cam (int2.F90:538-584): regular pass + Erf-attenuated pass (int_rys.F90:225-227)
+    screened with the attenuated Schwarz matrix (int2.F90:674-685), s..f shells, RHF and UROHF consumers."""
+    from openqp_b200.int2 import Int2RhfData, Int2UrohfData
+    bs, o = _pair(oracle_mod, drv, B.water_dimer(), "cc-pvtz", upload_q=True)
+    mu, alpha, beta = 0.33, 0.19, 0.46  # CAM-B3LYP
+    qa_o = o.schwarz_attenuated(mu)
+    qa_g = drv.set_screening_cam(mu)
+    assert np.abs(qa_g - qa_o).max() <= 1e-10 * max(1.0, qa_o.max())
+    drv.set_screening_cam(mu, qa_o)  # the oracle's bounds: the screening decisions must then be identical
+    d = pack(decaying_density(bs) * 1e-2)
+    c = drv.run(Int2RhfData(d, post=True), cam=True, alpha=alpha, beta=beta, mu=mu)
+    fo, st = o.fock_cam(d, alpha, beta, mu)
+    assert np.abs(c.f - fo).max() < FOCK_TOL
+    assert c.skipped == st["nschwz"] and st["nschwz"] > 0
+    # the attenuated pass alone (alpha = 0, no regular Coulomb): exercises the pass-2 integrals in isolation
+    c2 = drv.run(Int2RhfData(d, post=True), cam=True, alpha=0.0, beta=1.0, mu=mu, alpha_coulomb=0.0, beta_coulomb=1.0)
+    fo2, _ = o.fock_cam(d, 0.0, 1.0, mu, alpha_coulomb=0.0, beta_coulomb=1.0)
+    assert np.abs(c2.f - fo2).max() < FOCK_TOL and np.abs(fo2).max() > 1e-3
+    da, db = pack(random_sym_density(bs.nbf, 31, 0.05)), pack(random_sym_density(bs.nbf, 32, 0.05))
+    du = np.stack([da, db])
+    cu = drv.run(Int2UrohfData(du, post=True), cam=True, alpha=alpha, beta=beta, mu=mu)
+    fu, _ = o.fock_cam(du, alpha, beta, mu, urohf=True)
+    assert np.abs(cu.f - fu).max() < 2 * FOCK_TOL  # dense density, |D| ~ 0.15, |F| ~ 0.5
+    # a regular build afterwards is unaffected by the cached attenuated data
+    c3 = drv.run(Int2RhfData(d, post=True))
+    f3, _ = o.fock(d)
+    assert np.abs(c3.f - f3).max() < FOCK_TOL

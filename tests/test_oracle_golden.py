@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from common import golden, random_sym_density, rpa_energies
+from common import decaying_density, golden, random_sym_density, rpa_energies
 from openqp_b200 import basis as B
 from openqp_b200.scf import pack, scf, unpack
 
@@ -147,3 +147,64 @@ def test_screening_counts_consistent(oracle_mod):
     assert nschwz > 0 and n > 0
     f, st = o.fock(d)
     assert st["nschwz"] == nschwz and st["nquartets"] == n
+
+
+def test_oracle_attenuated_integrals_closed_form(oracle_mod):
+    """Erf-attenuated integrals of the CAM second pass (int_rys.F90:179-181, 225-227): contracted (ss|ss) integrals
+    against the closed form  sum_prims c_a c_b c_c c_d 2 pi^{5/2} / (zeta eta sqrt(ab')) K_ab K_cd F0(rho' |PQ|^2),
+    ab' = zeta + eta + zeta eta / mu^2, rho' = zeta eta / ab'; and the limits mu -> infinity (regular integrals)."""
+    from scipy.special import erf
+    bs = B.BasisSet(B.water_dimer(), "6-31g")
+    mu = 0.33
+    o = oracle_mod.Oracle(bs)
+    o.set_screening()
+    sshells = [i for i in range(bs.nshell) if bs.am[i] == 0]
+
+    def f0(x):
+        return 1.0 if x < 1e-14 else 0.5 * np.sqrt(np.pi / x) * erf(np.sqrt(x))
+
+    def prims(i):
+        g = bs.g_offset[i] - (1 if bs.g_offset.min() == 1 else 0)
+        return [(bs.ex[g + k], bs.cc[g + k]) for k in range(bs.ncontr[i])], np.asarray(bs.centers[i], dtype=float)
+
+    def closed(i, j, k, l, mu):
+        (pa, A), (pb, Bc), (pc, Cc), (pd, Dc) = prims(i), prims(j), prims(k), prims(l)
+        tot = 0.0
+        for a, ca in pa:
+            for b, cb in pb:
+                z = a + b
+                P = (a * A + b * Bc) / z
+                kab = np.exp(-a * b / z * np.dot(A - Bc, A - Bc))
+                for c, cc_ in pc:
+                    for d, cd in pd:
+                        e = c + d
+                        Q = (c * Cc + d * Dc) / e
+                        kcd = np.exp(-c * d / e * np.dot(Cc - Dc, Cc - Dc))
+                        ab = z + e + (z * e / mu ** 2 if mu > 0 else 0.0)
+                        rho = z * e / ab
+                        tot += ca * cb * cc_ * cd * 2 * np.pi ** 2.5 / (z * e * np.sqrt(ab)) * kab * kcd * f0(rho * np.dot(P - Q, P - Q))
+        return tot
+
+    quartets = [(sshells[0], sshells[1], sshells[2], sshells[3]), (sshells[4], sshells[0], sshells[5], sshells[2]),
+                (sshells[1], sshells[1], sshells[6], sshells[3])]
+    regs = []
+    for q in quartets:
+        reg = o.eri_block(*q).ravel()[0]
+        assert abs(reg - closed(*q, 0.0)) < 1e-12 * max(1.0, abs(reg))
+        regs.append(reg)
+    o.set_attenuation(mu)
+    for q, reg in zip(quartets, regs):
+        att = o.eri_block(*q).ravel()[0]
+        assert abs(att - closed(*q, mu)) < 1e-12 * max(1.0, abs(att))
+        assert 0 < att < reg  # erf(mu r)/r < 1/r
+    o.set_attenuation(1.0e6)  # erf(mu r) -> 1
+    for q in quartets:
+        assert abs(o.eri_block(*q).ravel()[0] - closed(*q, 0.0)) < 1e-9
+    o.set_attenuation(0.0)
+    # CAM with beta = 0 is the regular build; the attenuated Schwarz matrix is bounded by the regular one
+    d = pack(decaying_density(bs))
+    f0_, _ = o.fock(d, 0.25, 1.0)
+    f1_, _ = o.fock_cam(d, 0.25, 0.0, mu)
+    assert np.abs(f0_ - f1_).max() < 1e-13
+    qa = o.schwarz_attenuated(mu)
+    assert (qa <= o.schwarz * (1 + 1e-12) + 1e-300).all() and qa.max() > 0
