@@ -6,15 +6,20 @@
 //   (int2.F90:1187-1207, int_rys.F90:715-785) -> storeints (int2.F90:1741-1865) -> consumer update
 //   (int2.F90:1414-1578, tdhf_lib.F90:140-224, tdhf_mrsf_lib.F90:218-333).
 //
-// Mapping: a CTA owns QPB quartets; a quartet is owned by a team of TS = NA*NB*KS threads (one thread
-// per bra Cartesian component pair, optionally KS ket slices).  Per primitive quartet:
-//   B1  2R threads evaluate the Rys roots/weights (Chebyshev tables) into shared memory,
-//   B2  3R threads run the 2-D VRR and both HRR transfers for one (root, direction) each, in shared memory,
-//   B3  every thread accumulates its NC*ND/KS ket components in registers:  I += gx*gy*gz.
-// Then the Cartesian block goes to shared memory, is normalised / projected to pure functions index by
-// index (sparse tables), the element cutoff and the coincidence factors are applied, and the block is
-// contracted with the density: J and K partial sums are reduced in registers per output element and
-// leave the CTA as one FP64 red.global.add per Fock element per quartet.
+// Three kernel families, chosen per class at compile time (launch_eri):
+//   eri_small_kernel   one thread = one quartet; classes with <= 36 Cartesian integrals keep everything in registers,
+//                      classes with <= 150 keep the gx/gy/gz tables of a root in shared memory ([entry][thread]);
+//   eri_group_kernel   a quartet is owned by an aligned group of G = 4..32 lanes of one warp (__syncwarp only): roots,
+//                      2-D VRR + HRR per (root, direction) in registers, tables in shared memory ([c][d][a][b]),
+//                      register-tiled assembly, block projected and digested from shared memory;
+//   eri_kernel         CTA teams (NA*NB*KS threads per quartet, CTA barriers) for the few largest classes.
+// Per primitive quartet:  roots/weights (Chebyshev tables) -> 2-D VRR on centres A and C -> HRR to B and D ->
+// I += gx*gy*gz.  Then the Cartesian block is normalised / projected to pure functions index by index (sparse
+// compile-time tables), the element cutoff and the coincidence factors are applied, and the block is contracted with
+// the density: SYM consumers (RHF/UROHF) reduce per output element in registers and leave as one FP64
+// red.global.add per Fock element per quartet (after a segmented reduction over quartets of the warp that share the
+// output); GEN consumers (TD/MRSF, many general densities) are digested warp-cooperatively with DMMA m8n8k4.
+// mu2inv != 0 selects Erf-attenuated integrals (CAM second pass).
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -2070,6 +2075,16 @@ eri_group_kernel(const EriArgs A) {
   }
 }
 
+// cudaFuncSetAttribute is per device: remember per (kernel instantiation, device) whether the opt-in is done
+struct DevFlags {
+  bool done[64] = {};
+  bool& cur() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return done[dev & 63];
+  }
+};
+
 template <int LA, int LB, int LC, int LD, int PV>
 cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
   using Cfg = ClassCfg<LA, LB, LC, LD>;
@@ -2079,7 +2094,8 @@ cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
     constexpr size_t gen = (size_t)(SMALL_NT / 32) * gen_sub(NTOT, SMALL_NT / 32) * (NTOT | 1) * sizeof(double);  // MODE_GEN block staging
     const size_t smem = (RysSmem<R>::USE ? (size_t)RysSmem<R>::doubles(args.rys_xmax) * sizeof(double) : 0) +
                         (args.mode == MODE_GEN ? gen : 0);
-    static bool attr_set = false;
+    static DevFlags flags;
+    bool& attr_set = flags.cur();
     if (!attr_set && smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(eri_small_kernel<LA, LB, LC, LD, PV, false>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
@@ -2093,7 +2109,8 @@ cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
     constexpr size_t gen = (size_t)(MEDIUM_NT / 32) * gen_sub(NTOT, MEDIUM_NT / 32) * (NTOT | 1) * sizeof(double);  // MODE_GEN block staging
     constexpr size_t smem0 = (size_t)3 * Cfg::NIJ1 * Cfg::NKL1 * MEDIUM_NT * sizeof(double);
     const size_t smem = smem0 + (args.mode == MODE_GEN ? gen : 0);
-    static bool attr_set = false;
+    static DevFlags flags;
+    bool& attr_set = flags.cur();
     if (!attr_set && smem0 + gen > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(eri_small_kernel<LA, LB, LC, LD, PV, true>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem0 + gen));
@@ -2104,7 +2121,8 @@ cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
     return cudaGetLastError();
   } else if constexpr (GroupCfg<LA, LB, LC, LD>::OK) {
     using GC = GroupCfg<LA, LB, LC, LD>;
-    static bool attr_set = false;
+    static DevFlags flags;
+    bool& attr_set = flags.cur();
     if (!attr_set && GC::SMEM > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(eri_group_kernel<LA, LB, LC, LD, PV>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GC::SMEM);
@@ -2114,7 +2132,8 @@ cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
     eri_group_kernel<LA, LB, LC, LD, PV><<<nblocks, GC::NT, GC::SMEM, st>>>(args);
     return cudaGetLastError();
   } else {
-    static bool attr_set = false;
+    static DevFlags flags;
+    bool& attr_set = flags.cur();
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(eri_kernel<LA, LB, LC, LD, PV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)Cfg::SMEM);

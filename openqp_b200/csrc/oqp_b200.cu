@@ -831,7 +831,8 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   std::vector<float> chunk_ms;
   const size_t smem_rows = (size_t)2 * ns * sizeof(double);
   const int use_smem = smem_rows <= 96 * 1024;
-  static bool enum_attr = false;
+  static DevFlags enum_flags;  // per device
+  bool& enum_attr = enum_flags.cur();
   if (use_smem && smem_rows > 48 * 1024 && !enum_attr) {
     CK(cudaFuncSetAttribute(k_enum, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     enum_attr = true;
