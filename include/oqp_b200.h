@@ -111,6 +111,18 @@ int oqpb_jk_mrsf(oqpb_ctx* ctx, const double* d3, int nvec, int ncomp, double sc
 int oqpb_jk_mrsf_dev(oqpb_ctx* ctx, const double* d3_dev, int nvec, int ncomp, double scale_exchange,
                      double scale_coulomb, double* f3_dev);
 
+/* The response consumers through int2_run_cam (range-separated functionals):
+ *   TD   (tdhf_lib.F90:140-224): the same update in both passes, pass 2 with Erf-attenuated integrals and
+ *        (beta_coulomb, beta);
+ *   MRSF (tdhf_mrsf_lib.F90:279-326): pass 1 all components with (alpha_coulomb, alpha), pass 2 the exchange of
+ *        component 7 only with beta (ncomp must be 7).                                                    */
+int oqpb_jk_td_cam(oqpb_ctx* ctx, const double* d2, int nvec, int flags, double alpha, double beta, double mu,
+                   double alpha_coulomb, double beta_coulomb, double* apb, double* amb, long long* nskipped);
+int oqpb_jk_mrsf_cam(oqpb_ctx* ctx, const double* d3, int nvec, int ncomp, double alpha, double beta, double mu,
+                     double alpha_coulomb, double* f3, long long* nskipped);
+int oqpb_jk_mrsf_cam_dev(oqpb_ctx* ctx, const double* d3_dev, int nvec, int ncomp, double alpha, double beta,
+                         double mu, double alpha_coulomb, double* f3_dev);
+
 /* ---- introspection used by the parity tests and the benchmark ------------------------------------- */
 /* statistics of the last build: [0] surviving shell quartets, [1] skipped (nschwz), [2] primitive
  * quartets evaluated is not tracked (0), [3] kernel launches, [4] algorithmic FLOPs (SURVEY 8d-1 model,

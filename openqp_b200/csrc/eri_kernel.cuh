@@ -116,7 +116,9 @@ struct EriArgs {
   int gen_wantj[MAX_MATS];
   // batched GEN: matrices stored interleaved [a*nbf+b][nmat] when gen_interleaved != 0 (MRSF layout)
   int gen_interleaved;
-  int gen_nmat_total;  // nmat for interleaved layout (may exceed MAX_MATS)
+  int gen_nmat_total;  // nmat for interleaved layout (may exceed MAX_MATS): the stride between AO pairs
+  int gen_mcount;      // matrices that take the exchange part, starting at Pgen / Fgen (<= gen_nmat_total; the CAM second
+                       // pass of the MRSF consumer passes Pgen + 6 nvec and nvec: component 7 only)
   int gen_ncoul;       // interleaved: component index < gen_ncoul gets Coulomb (uses comp = m / nvec ... see kernel)
   int gen_nvec;
   const double* Pgen;  // interleaved density
@@ -758,7 +760,7 @@ __device__ __forceinline__ void digest_sym_group(const EriArgs& A, const double*
 template <int n0, int n1, int n2, int n3>
 __device__ __forceinline__ void digest_gen(const EriArgs& A, const double* blk, int o0, int o1, int o2, int o3, int t,
                                            int ts) {
-  const int nbf = A.nbf, NM = A.gen_nmat_total, nv = A.gen_nvec;
+  const int nbf = A.nbf, NM = A.gen_nmat_total, MC = A.gen_mcount, nv = A.gen_nvec;
   constexpr int n23 = n2 * n3;
   const double* __restrict__ P = A.Pgen;
   double* __restrict__ F = A.Fgen;
@@ -793,8 +795,8 @@ __device__ __forceinline__ void digest_gen(const EriArgs& A, const double* blk, 
     }
   }
   if (ck != 0.0) {
-    for (int e = t; e < n0 * n2 * NM; e += ts) {  // (a,c)
-      int m = e % NM, o = e / NM;
+    for (int e = t; e < n0 * n2 * MC; e += ts) {  // (a,c)
+      int m = e % MC, o = e / MC;
       int a = o / n2, c = o % n2;
       double s1 = 0.0, s2 = 0.0;
       for (int b = 0; b < n1; ++b) {
@@ -807,8 +809,8 @@ __device__ __forceinline__ void digest_gen(const EriArgs& A, const double* blk, 
       if (s1 != 0.0) FX(o0 + a, o2 + c, -ck * s1);
       if (s2 != 0.0) FX(o2 + c, o0 + a, -ck * s2);
     }
-    for (int e = t; e < n0 * n3 * NM; e += ts) {  // (a,d)
-      int m = e % NM, o = e / NM;
+    for (int e = t; e < n0 * n3 * MC; e += ts) {  // (a,d)
+      int m = e % MC, o = e / MC;
       int a = o / n3, d = o % n3;
       double s1 = 0.0, s2 = 0.0;
       for (int b = 0; b < n1; ++b) {
@@ -821,8 +823,8 @@ __device__ __forceinline__ void digest_gen(const EriArgs& A, const double* blk, 
       if (s1 != 0.0) FX(o0 + a, o3 + d, -ck * s1);
       if (s2 != 0.0) FX(o3 + d, o0 + a, -ck * s2);
     }
-    for (int e = t; e < n1 * n2 * NM; e += ts) {  // (b,c)
-      int m = e % NM, o = e / NM;
+    for (int e = t; e < n1 * n2 * MC; e += ts) {  // (b,c)
+      int m = e % MC, o = e / MC;
       int b = o / n2, c = o % n2;
       double s1 = 0.0, s2 = 0.0;
       for (int a = 0; a < n0; ++a) {
@@ -835,8 +837,8 @@ __device__ __forceinline__ void digest_gen(const EriArgs& A, const double* blk, 
       if (s1 != 0.0) FX(o1 + b, o2 + c, -ck * s1);
       if (s2 != 0.0) FX(o2 + c, o1 + b, -ck * s2);
     }
-    for (int e = t; e < n1 * n3 * NM; e += ts) {  // (b,d)
-      int m = e % NM, o = e / NM;
+    for (int e = t; e < n1 * n3 * MC; e += ts) {  // (b,d)
+      int m = e % MC, o = e / MC;
       int b = o / n3, d = o % n3;
       double s1 = 0.0, s2 = 0.0;
       for (int a = 0; a < n0; ++a) {
@@ -878,7 +880,7 @@ __device__ __forceinline__ void gen_contract(const EriArgs& A, const double* __r
   constexpr int KT = (NK + 3) / 4, OT = (NO + 7) / 8;
   constexpr bool USE_MMA = (double)(NO * NK) / (double)(OT * 8 * KT * 4) >= OQPB_DMMA_MIN_FILL;
   const int NM = A.gen_nmat_total;
-  const int mrows = COUL ? A.gen_ncoul * A.gen_nvec : NM;
+  const int mrows = COUL ? A.gen_ncoul * A.gen_nvec : A.gen_mcount;
   const double scale = COUL ? A.cj : -A.ck;
   if (mrows <= 0 || scale == 0.0) return;
   const size_t nbf = (size_t)A.nbf;

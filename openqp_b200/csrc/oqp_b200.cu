@@ -705,6 +705,7 @@ struct BuildSpec {
   const double* Pgen = nullptr;
   double* Fgen = nullptr;
   int gen_nm = 0, gen_ncoul = 0, gen_nvec = 0;
+  int gen_mcount = -1;  // matrices taking the exchange part (default: all gen_nm)
   double cj = 0, ck = 0;
   double digest_flops_per_int = 0;
   bool attenuated = false;  // CAM second pass: attenuated integrals + attenuated Schwarz bounds (ctx->run.att_mu)
@@ -873,6 +874,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     for (int m = 0; m < S.nmat; ++m) { A.DJ[m] = S.DJ[m]; A.DK[m] = S.DK[m]; A.F[m] = S.F[m]; }
     A.cj = S.cj; A.ck = S.ck;
     A.Pgen = S.Pgen; A.Fgen = S.Fgen; A.gen_nmat_total = S.gen_nm; A.gen_ncoul = S.gen_ncoul; A.gen_nvec = S.gen_nvec;
+    A.gen_mcount = S.gen_mcount >= 0 ? S.gen_mcount : S.gen_nm;
     const int qcls = quartet_class(pc_of(ch.pca), pc_of(ch.pcb));
     const ClassEntry& ce = tab[qcls];
     size_t nb = std::min<size_t>((ch.cand + ce.qpb - 1) / ce.qpb, (size_t)ce.maxcta * ctx->grid_pct / 100);
@@ -1268,13 +1270,12 @@ int oqpb_fock_cam(oqpb_ctx* ctx, int urohf, const double* d, double* f, int nfoc
 }
 
 // shared driver for the general-density consumers: X interleaved [(nu*nbf+mu)*NM + m]
-static int gen_build(oqpb_ctx* ctx, int NM, int ncoul, int nvec, double cj, double ck) {
-  const int ns = ctx->nshell, nbf = ctx->nbf;
-  const long npairs = (long)ns * (ns + 1) / 2;
-  (void)npairs;
-  CK(cudaMemsetAsync(ctx->d_gen_out.p, 0, (size_t)nbf * nbf * NM * sizeof(double), ctx->stream));
+static int gen_build(oqpb_ctx* ctx, int NM, int ncoul, int nvec, double cj, double ck, bool attenuated = false) {
+  const int nbf = ctx->nbf;
+  if (!attenuated) CK(cudaMemsetAsync(ctx->d_gen_out.p, 0, (size_t)nbf * nbf * NM * sizeof(double), ctx->stream));
   BuildSpec S;
   S.mode = MODE_GEN;
+  S.attenuated = attenuated;  // CAM second pass: accumulates on top of the first
   S.Pgen = ctx->d_gen_in.as<double>();
   S.Fgen = ctx->d_gen_out.as<double>();
   S.gen_nm = NM; S.gen_ncoul = ncoul; S.gen_nvec = nvec;
@@ -1283,11 +1284,14 @@ static int gen_build(oqpb_ctx* ctx, int NM, int ncoul, int nvec, double cj, doub
   return run_build(ctx, S);
 }
 
-int oqpb_jk_td(oqpb_ctx* ctx, const double* d2, int nvec, int flags, double se, double sc, double* apb, double* amb,
-               long long* nskipped) {
+// npass = 2: int2_run_cam with the TD consumer -- the same update in both passes with the pass's scale factors
+static int td_core(oqpb_ctx* ctx, const double* d2, int nvec, int flags, int npass, const double* sev, const double* scv,
+                   double mu, double* apb, double* amb, long long* nskipped) {
   int rc = check_ready(ctx);
   if (rc) return rc;
   cudaSetDevice(ctx->device);
+  if (npass == 2 && (rc = oqpb_set_screening_cam(ctx, mu, nullptr))) return rc;
+  const double se = sev[0], sc = scv[0];
   if (nvec < 1) return OQPB_ERR_BAD_ARG;
   const int ns = ctx->nshell, nbf = ctx->nbf;
   const long n2 = (long)nbf * nbf, npairs = (long)ns * (ns + 1) / 2;
@@ -1316,6 +1320,7 @@ int oqpb_jk_td(oqpb_ctx* ctx, const double* d2, int nvec, int flags, double se, 
     k_td_pack<<<gb, 256, 0, ctx->stream>>>(ctx->d_Din.as<double>(), ctx->d_gen_in.as<double>(), nbf, nvec, 1, 0);
     rc = gen_build(ctx, NM, (flags & OQPB_TD_TDA_COULOMB) ? 1 : 0, nvec, 2.0 * sc, se);
     if (rc) return rc;
+    if (npass == 2 && (rc = gen_build(ctx, NM, (flags & OQPB_TD_TDA_COULOMB) ? 1 : 0, nvec, 2.0 * scv[1], sev[1], true))) return rc;
     k_td_unpack<<<gb, 256, 0, ctx->stream>>>(ctx->d_gen_out.as<double>(), ctx->d_Din.as<double>(), nbf, nvec, NM, 0);
     CK(cudaMemcpyAsync(amb, ctx->d_Din.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   } else {
@@ -1323,6 +1328,7 @@ int oqpb_jk_td(oqpb_ctx* ctx, const double* d2, int nvec, int flags, double se, 
     k_td_pack<<<gb, 256, 0, ctx->stream>>>(ctx->d_Din.as<double>(), ctx->d_gen_in.as<double>(), nbf, nvec, 2, 1);
     rc = gen_build(ctx, NM, want_apb ? 1 : 0, nvec, 2.0 * sc, se);
     if (rc) return rc;
+    if (npass == 2 && (rc = gen_build(ctx, NM, want_apb ? 1 : 0, nvec, 2.0 * scv[1], sev[1], true))) return rc;
     if (want_apb) {
       k_td_unpack<<<gb, 256, 0, ctx->stream>>>(ctx->d_gen_out.as<double>(), ctx->d_Din.as<double>(), nbf, nvec, NM, 0);
       CK(cudaMemcpyAsync(apb, ctx->d_Din.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1338,8 +1344,25 @@ int oqpb_jk_td(oqpb_ctx* ctx, const double* d2, int nvec, int flags, double se, 
   return OQPB_OK;
 }
 
-// d3 / f3 on the device (interleaved d3(v, c, mu, nu), v fastest)
-static int mrsf_core(oqpb_ctx* ctx, const double* d3_dev, double* f3_dev, int nvec, int ncomp, double se, double sc) {
+int oqpb_jk_td(oqpb_ctx* ctx, const double* d2, int nvec, int flags, double se, double sc, double* apb, double* amb,
+               long long* nskipped) {
+  return td_core(ctx, d2, nvec, flags, 1, &se, &sc, 0.0, apb, amb, nskipped);
+}
+int oqpb_jk_td_cam(oqpb_ctx* ctx, const double* d2, int nvec, int flags, double alpha, double beta, double mu,
+                   double alpha_coulomb, double beta_coulomb, double* apb, double* amb, long long* nskipped) {
+  const double se[2] = {alpha, beta}, sc[2] = {alpha_coulomb, beta_coulomb};
+  return td_core(ctx, d2, nvec, flags, 2, se, sc, mu, apb, amb, nskipped);
+}
+
+// d3 / f3 on the device (interleaved d3(v, c, mu, nu), v fastest).  npass = 2: int2_run_cam, pass 2 = attenuated
+// integrals, exchange of component 7 only (tdhf_mrsf_lib.F90:312-326)
+static int mrsf_core(oqpb_ctx* ctx, const double* d3_dev, double* f3_dev, int nvec, int ncomp, double se, double sc,
+                     int npass = 1, double se2 = 0.0, double mu = 0.0) {
+  if (npass == 2) {
+    if (ncomp < 7) return OQPB_ERR_BAD_ARG;
+    int rc0 = oqpb_set_screening_cam(ctx, mu, nullptr);
+    if (rc0) return rc0;
+  }
   const int ns = ctx->nshell, nbf = ctx->nbf;
   const long npairs = (long)ns * (ns + 1) / 2;
   const int NM = nvec * ncomp;
@@ -1357,7 +1380,20 @@ static int mrsf_core(oqpb_ctx* ctx, const double* d3_dev, double* f3_dev, int nv
   S.gen_nm = NM; S.gen_ncoul = 4; S.gen_nvec = nvec;
   S.cj = sc; S.ck = se;
   S.digest_flops_per_int = 144.0 / 7.0 * NM;  // (4*4 + 8*7) * 2 flops per integral and vector
-  return run_build(ctx, S);
+  int rc = run_build(ctx, S);
+  if (rc || npass == 1) return rc;
+  const double kernel_ms = ctx->st_kernel_ms, flops = ctx->st_flops;
+  const long long surv = ctx->st_survivors, launches = ctx->st_launches;
+  S.attenuated = true;
+  S.Pgen = d3_dev + (size_t)6 * nvec;  // component 7 (m = 6 nvec .. 7 nvec - 1), same AO-pair stride NM
+  S.Fgen = f3_dev + (size_t)6 * nvec;
+  S.gen_ncoul = 0;
+  S.gen_mcount = nvec;
+  S.cj = 0.0; S.ck = se2;
+  S.digest_flops_per_int = 16.0 * nvec;
+  if ((rc = run_build(ctx, S))) return rc;
+  ctx->st_kernel_ms += kernel_ms; ctx->st_flops += flops; ctx->st_survivors += surv; ctx->st_launches += launches;
+  return OQPB_OK;
 }
 
 int oqpb_jk_mrsf_dev(oqpb_ctx* ctx, const double* d3_dev, int nvec, int ncomp, double se, double sc, double* f3_dev) {
@@ -1368,8 +1404,17 @@ int oqpb_jk_mrsf_dev(oqpb_ctx* ctx, const double* d3_dev, int nvec, int ncomp, d
   return mrsf_core(ctx, d3_dev, f3_dev, nvec, ncomp, se, sc);
 }
 
-int oqpb_jk_mrsf(oqpb_ctx* ctx, const double* d3, int nvec, int ncomp, double se, double sc, double* f3,
-                 long long* nskipped) {
+int oqpb_jk_mrsf_cam_dev(oqpb_ctx* ctx, const double* d3_dev, int nvec, int ncomp, double alpha, double beta, double mu,
+                         double alpha_coulomb, double* f3_dev) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  cudaSetDevice(ctx->device);
+  if (nvec < 1 || ncomp < 7 || !d3_dev || !f3_dev) return OQPB_ERR_BAD_ARG;
+  return mrsf_core(ctx, d3_dev, f3_dev, nvec, ncomp, alpha, alpha_coulomb, 2, beta, mu);
+}
+
+static int mrsf_host(oqpb_ctx* ctx, const double* d3, int nvec, int ncomp, double se, double sc, double* f3,
+                     long long* nskipped, int npass, double se2, double mu) {
   int rc = check_ready(ctx);
   if (rc) return rc;
   cudaSetDevice(ctx->device);
@@ -1380,12 +1425,21 @@ int oqpb_jk_mrsf(oqpb_ctx* ctx, const double* d3, int nvec, int ncomp, double se
   CK(ctx->d_gen_in.ensure(bytes));
   CK(ctx->d_gen_out.ensure(bytes));
   CK(cudaMemcpyAsync(ctx->d_gen_in.p, d3, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  rc = mrsf_core(ctx, ctx->d_gen_in.as<double>(), ctx->d_gen_out.as<double>(), nvec, ncomp, se, sc);
+  rc = mrsf_core(ctx, ctx->d_gen_in.as<double>(), ctx->d_gen_out.as<double>(), nvec, ncomp, se, sc, npass, se2, mu);
   if (rc) return rc;
   CK(cudaMemcpyAsync(f3, ctx->d_gen_out.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (nskipped) *nskipped = ctx->st_skipped;
   return OQPB_OK;
+}
+
+int oqpb_jk_mrsf(oqpb_ctx* ctx, const double* d3, int nvec, int ncomp, double se, double sc, double* f3,
+                 long long* nskipped) {
+  return mrsf_host(ctx, d3, nvec, ncomp, se, sc, f3, nskipped, 1, 0.0, 0.0);
+}
+int oqpb_jk_mrsf_cam(oqpb_ctx* ctx, const double* d3, int nvec, int ncomp, double alpha, double beta, double mu,
+                     double alpha_coulomb, double* f3, long long* nskipped) {
+  return mrsf_host(ctx, d3, nvec, ncomp, alpha, alpha_coulomb, f3, nskipped, 2, beta, mu);
 }
 
 int oqpb_last_stats(oqpb_ctx* ctx, long long* s) {

@@ -127,10 +127,10 @@ class Int2Compute:
     # -- int2_compute_t%run (int2.F90:500-536, 589) -----------------------------------------------
     def run(self, consumer, cam=False, alpha=1.0, beta=0.0, mu=0.0, alpha_coulomb=1.0, beta_coulomb=0.0):
         """run(consumer): one pass with the consumer's scale factors.  run(consumer, cam=True, alpha, beta, mu): the
-        range-separated two-pass build int2_run_cam (int2.F90:538-584); SCF consumers only (RHF / UROHF)."""
+        range-separated two-pass build int2_run_cam (int2.F90:538-584) for every consumer."""
         if cam:
             if not hasattr(consumer, "_run_cam"):
-                raise Int2Error("cam=True is implemented for Int2RhfData / Int2UrohfData")
+                raise Int2Error("consumer without a CAM path")
             consumer._run_cam(self, alpha, beta, mu, alpha_coulomb, beta_coulomb)
         else:
             consumer._run(self)
@@ -301,6 +301,21 @@ class Int2TdData:
         self.amb = np.transpose(amb, (0, 2, 1)).copy()
         self.skipped = int(ns.value)
 
+    def _run_cam(self, drv: Int2Compute, alpha, beta, mu, alpha_coulomb, beta_coulomb):
+        nv, nbf, _ = self.d2.shape
+        dF = np.ascontiguousarray(np.transpose(self.d2, (0, 2, 1)))
+        apb = np.zeros_like(dF)
+        amb = np.zeros_like(dF)
+        flags = ((OQPB_TD_APB if self.int_apb else 0) | (OQPB_TD_AMB if self.int_amb else 0) |
+                 (OQPB_TD_TDA if self.tamm_dancoff else 0) | (OQPB_TD_TDA_COULOMB if self.tamm_dancoff_coulomb else 0))
+        ns = C.c_longlong(0)
+        drv._check(lib().oqpb_jk_td_cam(drv._h, _dp(dF), C.c_int(nv), C.c_int(flags), C.c_double(alpha), C.c_double(beta),
+                                        C.c_double(mu), C.c_double(alpha_coulomb), C.c_double(beta_coulomb), _dp(apb),
+                                        _dp(amb), C.byref(ns)), "oqpb_jk_td_cam")
+        self.apb = np.transpose(apb, (0, 2, 1)).copy()
+        self.amb = np.transpose(amb, (0, 2, 1)).copy()
+        self.skipped = int(ns.value)
+
 
 class Int2MrsfData:
     """int2_mrsf_data_t (tdhf_mrsf_lib.F90:8-26).  d3: (nvec, ncomp, nbf, nbf) [v, c, mu, nu]; f3 likewise."""
@@ -328,3 +343,19 @@ def fock_jk(drv: Int2Compute, d, scale_exchange=1.0, scale_coulomb=1.0, urohf=Fa
     cons = (Int2UrohfData if urohf else Int2RhfData)(d, scale_exchange, scale_coulomb, post=True)
     drv.run(cons)
     return cons.f, cons.skipped
+
+
+def _mrsf_run_cam(self, drv: Int2Compute, alpha, beta, mu, alpha_coulomb, beta_coulomb):
+    """pass 1 all components (alpha_coulomb, alpha); pass 2 attenuated exchange of component 7 only with beta
+    (tdhf_mrsf_lib.F90:312-326; beta_coulomb is not used by this consumer)"""
+    nv, nc, nbf, _ = self.d3.shape
+    dF = np.ascontiguousarray(np.transpose(self.d3, (3, 2, 1, 0)))
+    f3 = np.zeros_like(dF)
+    ns = C.c_longlong(0)
+    drv._check(lib().oqpb_jk_mrsf_cam(drv._h, _dp(dF), C.c_int(nv), C.c_int(nc), C.c_double(alpha), C.c_double(beta),
+                                      C.c_double(mu), C.c_double(alpha_coulomb), _dp(f3), C.byref(ns)), "oqpb_jk_mrsf_cam")
+    self.f3 = np.transpose(f3, (3, 2, 1, 0)).copy()
+    self.skipped = int(ns.value)
+
+
+Int2MrsfData._run_cam = _mrsf_run_cam

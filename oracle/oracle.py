@@ -159,15 +159,40 @@ class Oracle:
             lib().orc_td_post(C.c_int(nbf), C.c_int(nv), _p(apb))
         return np.transpose(apb, (0, 2, 1)).copy(), np.transpose(amb, (0, 2, 1)).copy(), st
 
-    def mrsf(self, d3, scale_exchange=1.0, scale_coulomb=1.0, nthreads=0, stride=1, offset=0):
+    def mrsf(self, d3, scale_exchange=1.0, scale_coulomb=1.0, nthreads=0, stride=1, offset=0, cur_pass=1):
         """int2_mrsf_data_t (tdhf_mrsf_lib.F90:8-26): d3 numpy (nvec, ncomp, nbf, nbf) [v,c,mu,nu];
         returns f3 same shape."""
         d3 = np.asarray(d3, dtype=np.float64)
         nv, nc, nbf, _ = d3.shape
         dF = np.ascontiguousarray(np.transpose(d3, (3, 2, 1, 0)))  # Fortran d3(v,c,mu,nu): v fastest
         f3 = np.zeros_like(dF)
-        st = self._run(MRSF, dF, nv, nc, scale_exchange, scale_coulomb, 0, f3, None, nthreads, 0, -1, stride, offset)
+        st = self._run(MRSF, dF, nv, nc, scale_exchange, scale_coulomb, 16 if cur_pass == 2 else 0, f3, None, nthreads, 0, -1,
+                       stride, offset)
         return np.transpose(f3, (3, 2, 1, 0)).copy(), st
+
+    def mrsf_cam(self, d3, alpha, beta, mu, alpha_coulomb=1.0, beta_coulomb=0.0, nthreads=0):
+        """int2_run_cam with the MRSF consumer: pass 1 regular (all components), pass 2 attenuated integrals, exchange of
+        component 7 only (tdhf_mrsf_lib.F90:312-326)."""
+        f1, _ = self.mrsf(d3, alpha, alpha_coulomb, nthreads=nthreads)
+        self.set_attenuation(mu)
+        try:
+            f2, st = self.mrsf(d3, beta, beta_coulomb, nthreads=nthreads, cur_pass=2)
+        finally:
+            self.set_attenuation(0.0)
+        return f1 + f2, st
+
+    def td_cam(self, d2, alpha, beta, mu, alpha_coulomb=1.0, beta_coulomb=0.0, nthreads=0, **kw):
+        """int2_run_cam with the TD consumer: the same update in both passes with the pass's scale factors
+        (tdhf_lib.F90:140-224); the stop-time symmetrisation of apb is applied once to the sum."""
+        a1, b1, _ = self.td(d2, alpha, alpha_coulomb, nthreads=nthreads, post=False, **kw)
+        self.set_attenuation(mu)
+        try:
+            a2, b2, st = self.td(d2, beta, beta_coulomb, nthreads=nthreads, post=False, **kw)
+        finally:
+            self.set_attenuation(0.0)
+        apb = np.ascontiguousarray(np.transpose(a1 + a2, (0, 2, 1)))
+        lib().orc_td_post(C.c_int(self.basis.nbf), C.c_int(apb.shape[0]), _p(apb))
+        return np.transpose(apb, (0, 2, 1)).copy(), b1 + b2, st
 
     def quartet_list(self, d_packed, want_list=True):
         d = np.ascontiguousarray(np.atleast_2d(d_packed), dtype=np.float64)

@@ -601,6 +601,7 @@ struct Consumer {
   int int_apb = 1, int_amb = 0, tda = 0, tda_coulomb = 0;
   // MRSF: d3(nvec, ncomp, nbf, nbf), v fastest
   int ncomp = 7;
+  int cur_pass = 1;  // multipass (CAM): pass 2 of the MRSF consumer touches only component 7 (tdhf_mrsf_lib.F90:312-326)
   std::vector<double> ds;
   std::vector<double> dsh;
   double max_den = 0;
@@ -705,12 +706,13 @@ void update(const Consumer &c, Buf &buf, double *f, double *f2, std::vector<int1
       int i = buf.ids[4 * n], j = buf.ids[4 * n + 1], k = buf.ids[4 * n + 2], l = buf.ids[4 * n + 3];
       double val = buf.ints[n];
       double xval = val * c.se, cval = val * c.sc;
+      if (c.cur_pass == 1)
       for (int cc = 0; cc < 4; cc++)
         for (int v = 0; v < nf; v++) {
           F3(v, cc, i, j) += cval * DS(v, cc, k, l); F3(v, cc, j, i) += cval * DS(v, cc, k, l);
           F3(v, cc, k, l) += cval * DS(v, cc, i, j); F3(v, cc, l, k) += cval * DS(v, cc, i, j);
         }
-      for (int cc = 0; cc < nc; cc++)
+      for (int cc = (c.cur_pass == 2 ? 6 : 0); cc < nc; cc++)  // pass 2: exchange of component 7 only (:312-326)
         for (int v = 0; v < nf; v++) {
           F3(v, cc, i, k) -= xval * D3(v, cc, j, l); F3(v, cc, k, i) -= xval * D3(v, cc, l, j);
           F3(v, cc, i, l) -= xval * D3(v, cc, j, k); F3(v, cc, l, i) -= xval * D3(v, cc, k, j);
@@ -1104,6 +1106,7 @@ void orc_run(void *h, int kind, const double *d, int nfocks, int ncomp, double s
   Consumer c;
   c.kind = kind; c.nbf = o->b.nbf; c.nfocks = nfocks; c.se = se; c.sc = sc; c.d = d; c.ncomp = ncomp;
   c.int_apb = flags & 1; c.int_amb = (flags >> 1) & 1; c.tda = (flags >> 2) & 1; c.tda_coulomb = (flags >> 3) & 1;
+  c.cur_pass = (flags >> 4) & 1 ? 2 : 1;
   size_t nbf = c.nbf, ntri = nbf * (nbf + 1) / 2, fs = 0, f2s = 0;
   if (kind == RHF || kind == UROHF) fs = ntri * nfocks;
   if (kind == TD) { fs = nbf * nbf * nfocks; f2s = fs; }

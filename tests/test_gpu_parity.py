@@ -360,3 +360,24 @@ def test_cam_two_pass_build(oracle_mod, drv):
     c3 = drv.run(Int2RhfData(d, post=True))
     f3, _ = o.fock(d)
     assert np.abs(c3.f - f3).max() < FOCK_TOL
+
+
+def test_cam_response_consumers(oracle_mod, drv):
+    """int2_run_cam with the TD consumer (same update in both passes) and the MRSF consumer (pass 2 = attenuated
+    exchange of component 7 only, tdhf_mrsf_lib.F90:312-326)."""
+    from openqp_b200.int2 import Int2MrsfData, Int2TdData
+    bs, o = _pair(oracle_mod, drv, B.water_dimer(), "6-31g(d)", upload_q=True)
+    mu, alpha, beta = 0.33, 0.19, 0.46
+    drv.set_screening_cam(mu, o.schwarz_attenuated(mu))  # identical bounds on both sides: identical quartet lists
+    rng = np.random.default_rng(3)
+    d3 = rng.normal(size=(3, 7, bs.nbf, bs.nbf)) * 0.1
+    c = drv.run(Int2MrsfData(d3), cam=True, alpha=alpha, beta=beta, mu=mu)
+    f3, _ = o.mrsf_cam(d3, alpha, beta, mu)
+    assert np.abs(c.f3 - f3).max() < FOCK_TOL
+    f3_reg, _ = o.mrsf(d3, alpha, 1.0)
+    assert np.abs(f3[:, :6] - f3_reg[:, :6]).max() < 1e-14 and np.abs(f3[:, 6] - f3_reg[:, 6]).max() > 1e-4
+    d2 = rng.normal(size=(2, bs.nbf, bs.nbf)) * 0.1
+    ct = drv.run(Int2TdData(d2, int_apb=True, int_amb=True), cam=True, alpha=alpha, beta=beta, mu=mu)
+    apb, amb, _ = o.td_cam(d2, alpha, beta, mu, int_apb=True, int_amb=True)
+    assert np.abs(ct.amb - amb).max() < FOCK_TOL, np.abs(ct.amb - amb).max()
+    assert np.abs(ct.apb - apb).max() < FOCK_TOL, np.abs(ct.apb - apb).max()
