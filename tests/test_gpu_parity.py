@@ -381,3 +381,45 @@ def test_cam_response_consumers(oracle_mod, drv):
     apb, amb, _ = o.td_cam(d2, alpha, beta, mu, int_apb=True, int_amb=True)
     assert np.abs(ct.amb - amb).max() < FOCK_TOL, np.abs(ct.amb - amb).max()
     assert np.abs(ct.apb - apb).max() < FOCK_TOL, np.abs(ct.apb - apb).max()
+
+
+def test_edge_cases(oracle_mod, drv):
+    """Degenerate inputs: a one-shell basis, shell pairs without surviving primitives (centres 60 bohr apart), a zero
+    density (every bra pair skipped), the maximum number of Fock matrices, a density count that is not a multiple of any
+    tile (MRSF, 10 x 7 = 70 matrices), and a build after a zero build (plan cache keyed on the density bound)."""
+    from openqp_b200.int2 import Int2MrsfData, Int2RhfData
+    # (1) hydrogen atom, STO-3G: one s shell, one quartet
+    h = B.Molecule(np.array([1]), np.zeros((1, 3)), "H")
+    bs = B.BasisSet(h, "sto-3g")
+    o = oracle_mod.Oracle(bs); q = o.set_screening()
+    drv.init(bs); drv.set_screening(q)
+    d = np.array([[0.7]])
+    c = drv.run(Int2RhfData(d, post=True))
+    fo, st = o.fock(d)
+    assert bs.nshell == 1 and np.abs(c.f - fo).max() < 1e-13 and c.skipped == st["nschwz"] == 0
+    # (2) two water molecules 60 bohr apart: inter-molecular shell pairs lose all their primitives
+    w = B.water()
+    far = B.Molecule(np.concatenate([w.Z, w.Z]), np.concatenate([w.xyz, w.xyz + np.array([60.0, 0.0, 0.0])]), "far dimer")
+    bs = B.BasisSet(far, "cc-pvdz")
+    o = oracle_mod.Oracle(bs); q = o.set_screening()
+    drv.init(bs); drv.set_screening(q)
+    assert (q[:bs.nshell // 2, bs.nshell // 2:] == 0).any()
+    dm = pack(random_sym_density(bs.nbf, 5, 0.1))
+    # (3) zero density first: everything is skipped at the bra level, F = 0
+    z = drv.run(Int2RhfData(np.zeros_like(dm), post=True))
+    _, stz = o.fock(np.zeros_like(dm))
+    assert np.abs(z.f).max() == 0.0 and z.skipped == stz["nschwz"] and drv.last_stats()["nquartets"] == 0
+    c = drv.run(Int2RhfData(dm, post=True))
+    fo, st = o.fock(dm)
+    assert np.abs(c.f - fo).max() < FOCK_TOL and c.skipped == st["nschwz"]
+    # (4) seven Fock matrices in one pass (MAX_MATS - 1)
+    ds = np.stack([pack(random_sym_density(bs.nbf, 40 + k, 0.1)) for k in range(7)])
+    c7 = drv.run(Int2RhfData(ds, scale_exchange=0.3, post=True))
+    f7, _ = o.fock(ds, 0.3)
+    assert np.abs(c7.f - f7).max() < FOCK_TOL
+    # (5) 70 general densities
+    rng = np.random.default_rng(9)
+    d3 = rng.normal(size=(10, 7, bs.nbf, bs.nbf)) * 0.05
+    cm = drv.run(Int2MrsfData(d3, scale_exchange=0.5, scale_coulomb=1.0))
+    fm, stm = o.mrsf(d3, 0.5, 1.0)
+    assert np.abs(cm.f3 - fm).max() < FOCK_TOL and cm.skipped == stm["nschwz"]
