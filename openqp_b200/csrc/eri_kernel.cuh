@@ -212,6 +212,16 @@ struct QInfo {  // 64 ints per quartet in shared memory
 
 // ---------------------------------------------------------------------------------------------------
 // roots / weights for function f (f < R: root t^2, f >= R: weight) at X
+// Table format per nroots: unit X intervals with 12-term Chebyshev fits; nroots = 1 ((ss|ss), (ps|ss): the most
+// heavily contracted classes, where the interpolation is a third of the FP64 work) uses quarter-width intervals with
+// 8 terms (tools/gen_rys_tables_fine.py, fit error < 2e-15): -4 % on those classes.  The same format for nroots = 2
+// was measured slower: its 51 KB table per CTA eats the L1 of the 128-register classes.
+constexpr int RYS_FINE_MAXR = 1;
+template <int R>
+struct RysFmt {
+  static constexpr int NC = R <= RYS_FINE_MAXR ? 8 : 12;  // coefficients per function and interval
+  static constexpr int DIV = R <= RYS_FINE_MAXR ? 4 : 1;  // intervals per unit of X
+};
 template <int R>
 __device__ __forceinline__ double rys_eval(const EriArgs& a, double X, int f) {
   if (X >= (double)a.rys_xmax) {
@@ -219,13 +229,15 @@ __device__ __forceinline__ double rys_eval(const EriArgs& a, double X, int f) {
     if (f < R) return a.herm_r[f] / X;
     return a.herm_w[f - R] * rsqrt(X);
   }
-  int iv = (int)X;
-  double t = 2.0 * (X - (double)iv) - 1.0;
-  const double* c = a.rys_tab + ((size_t)iv * (2 * R) + f) * 12;
+  constexpr int NCF = RysFmt<R>::NC;
+  const double xs = X * RysFmt<R>::DIV;
+  int iv = (int)xs;
+  double t = 2.0 * (xs - (double)iv) - 1.0;
+  const double* c = a.rys_tab + ((size_t)iv * (2 * R) + f) * NCF;
   // Clenshaw
   double b1 = 0.0, b2 = 0.0, t2 = 2.0 * t;
 #pragma unroll
-  for (int k = 11; k >= 1; --k) {
+  for (int k = NCF - 1; k >= 1; --k) {
     double b0 = fma(t2, b1, __ldg(c + k) - b2);
     b2 = b1;
     b1 = b0;
@@ -1385,6 +1397,7 @@ __device__ __forceinline__ double rsqrt_nr(double x) {
   y = fma(y, e, y);
   return y;
 }
+template <int R>
 __device__ __forceinline__ RysX rys_prepare(const EriArgs& a, double X) {
   RysX s;
   s.asym = X >= (double)a.rys_xmax;
@@ -1394,18 +1407,20 @@ __device__ __forceinline__ RysX rys_prepare(const EriArgs& a, double X) {
     s.rs = rsqrt_nr(X);  // half-range Gauss-Hermite asymptote (rys.F90:2711-2713): r = h_r / X, w = h_w / sqrt(X)
     s.rx = s.rs * s.rs;
   } else {
-    s.iv = (int)X;
-    s.t = 2.0 * (X - (double)s.iv) - 1.0;
+    const double xs = X * RysFmt<R>::DIV;
+    s.iv = (int)xs;
+    s.t = 2.0 * (xs - (double)s.iv) - 1.0;
   }
   return s;
 }
-// Chebyshev table of one nroots in shared memory: per unit interval 2R functions x 12 coefficients, padded by
+// Chebyshev table of one nroots in shared memory: per interval 2R functions x NC coefficients, padded by
 // 2 doubles so that the 16-byte reads of lanes in different intervals fall into different banks
 template <int R>
 struct RysSmem {
-  static constexpr int STRIDE = 24 * R + 2;
+  static constexpr int ROW = 2 * R * RysFmt<R>::NC;
+  static constexpr int STRIDE = ROW + 2;
   static constexpr bool USE = R <= 3;
-  __host__ __device__ static constexpr int doubles(int xmax) { return xmax * STRIDE; }
+  __host__ __device__ static constexpr int doubles(int xmax) { return xmax * RysFmt<R>::DIV * STRIDE; }
 };
 // root r (as t^2) and its weight: two interleaved Clenshaw recurrences over 16-byte table loads
 template <int R, bool SM>
@@ -1416,22 +1431,23 @@ __device__ __forceinline__ void rys_pair(const EriArgs& a, const double* __restr
     w = a.herm_w[r] * s.rs;
     return;
   }
-  double2 p[6], q[6];
+  constexpr int NCF = RysFmt<R>::NC, H = NCF / 2;
+  double2 p[H], q[H];
   if constexpr (SM) {
-    const double2* ct = reinterpret_cast<const double2*>(stab + s.iv * RysSmem<R>::STRIDE + r * 12);
-    const double2* cw = ct + 6 * R;
+    const double2* ct = reinterpret_cast<const double2*>(stab + s.iv * RysSmem<R>::STRIDE + r * NCF);
+    const double2* cw = ct + H * R;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { p[k] = ct[k]; q[k] = cw[k]; }
+    for (int k = 0; k < H; ++k) { p[k] = ct[k]; q[k] = cw[k]; }
   } else {
-    const double2* __restrict__ ct = reinterpret_cast<const double2*>(a.rys_tab + ((size_t)s.iv * (2 * R) + r) * 12);
-    const double2* __restrict__ cw = ct + 6 * R;
+    const double2* __restrict__ ct = reinterpret_cast<const double2*>(a.rys_tab + ((size_t)s.iv * (2 * R) + r) * NCF);
+    const double2* __restrict__ cw = ct + H * R;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { p[k] = __ldg(ct + k); q[k] = __ldg(cw + k); }
+    for (int k = 0; k < H; ++k) { p[k] = __ldg(ct + k); q[k] = __ldg(cw + k); }
   }
   const double x2 = 2.0 * s.t;
   double b1 = 0.0, b2 = 0.0, e1 = 0.0, e2 = 0.0;
 #pragma unroll
-  for (int k = 11; k >= 1; --k) {
+  for (int k = NCF - 1; k >= 1; --k) {
     const double ck = (k & 1) ? p[k >> 1].y : p[k >> 1].x;
     const double dk = (k & 1) ? q[k >> 1].y : q[k >> 1].x;
     const double b0 = fma(x2, b1, ck - b2);
@@ -1457,8 +1473,9 @@ eri_small_kernel(const EriArgs A) {
   unsigned long long st_prim = 0, st_ints = 0;
   constexpr bool RSM = !GS && RysSmem<R>::USE;  // Rys table of this nroots staged in shared memory
   if constexpr (RSM) {
-    const int nint = A.rys_xmax;
-    for (int i = threadIdx.x; i < nint * 24 * R; i += NTH) gsm[(i / (24 * R)) * RysSmem<R>::STRIDE + i % (24 * R)] = A.rys_tab[i];
+    const int nint = A.rys_xmax * RysFmt<R>::DIV;
+    for (int i = threadIdx.x; i < nint * RysSmem<R>::ROW; i += NTH)
+      gsm[(i / RysSmem<R>::ROW) * RysSmem<R>::STRIDE + i % RysSmem<R>::ROW] = A.rys_tab[i];
     __syncthreads();
   }
   const int lane = threadIdx.x & 31;
@@ -1539,7 +1556,7 @@ eri_small_kernel(const EriArgs A) {
         const double X = rho * (PQ[0] * PQ[0] + PQ[1] * PQ[1] + PQ[2] * PQ[2]);
         const double pref = pfac * rsab;
         const double rz = rho * zinv, re = rho * einv, hz = 0.5 * zinv, he = 0.5 * einv;
-        const RysX rx = rys_prepare(A, X);
+        const RysX rx = rys_prepare<R>(A, X);
 #pragma unroll 1
         for (int r = 0; r < R; ++r) {
           double t2, w;

@@ -24,6 +24,7 @@
 #include "../../include/oqp_b200.h"
 #include "eri_kernel.cuh"
 #include "rys_tables.inc"
+#include "rys_tables_fine.inc"
 
 using namespace oqpb;
 
@@ -612,6 +613,14 @@ int build_pairtable(oqpb_ctx* ctx, const Cutoffs& c, PairTable& T, const std::ve
   return OQPB_OK;
 }
 
+// table of one nroots: the fine format (RysFmt<R>, quarter intervals x 8 terms) for nroots <= RYSF_MAXR
+static_assert(RYS_FINE_MAXR <= RYSF_MAXR && RYSF_NCOEF == RysFmt<1>::NC && RYSF_DIV == RysFmt<1>::DIV &&
+                  RYS_NCOEF == RysFmt<3>::NC,
+              "rys_tables*.inc and RysFmt disagree");
+const double* rys_table(oqpb_ctx* ctx, int R) {
+  return R <= RYS_FINE_MAXR ? ctx->d_rys.as<double>() + RYS_NTAB + RYSF_OFF_H[R - 1] : ctx->d_rys.as<double>() + RYS_OFF_H[R - 1];
+}
+
 void fill_common_args(oqpb_ctx* ctx, const PairTable& T, int la_, int lb_, EriArgs& A) {
   memset(&A, 0, sizeof A);
   A.bra = T.d_ent.as<PairEntry>() + T.cls_off[la_];
@@ -621,7 +630,7 @@ void fill_common_args(oqpb_ctx* ctx, const PairTable& T, int la_, int lb_, EriAr
   A.xyz = ctx->d_xyz.as<double>();
   A.aooff = ctx->d_aooff.as<int>();
   int R = (PC_LA[pca] + PC_LB[pca] + PC_LA[pcb] + PC_LB[pcb]) / 2 + 1;
-  A.rys_tab = ctx->d_rys.as<double>() + RYS_OFF_H[R - 1];
+  A.rys_tab = rys_table(ctx, R);
   A.rys_xmax = RYS_XMAX_H[R - 1];
   for (int k = 0; k < 7; ++k) { A.herm_r[k] = RYS_HERM_R_H[R - 1][k]; A.herm_w[k] = RYS_HERM_W_H[R - 1][k]; }
   A.nbf = ctx->nbf;
@@ -996,8 +1005,9 @@ int oqpb_ctx_create(oqpb_ctx** out, int device) {
   if (const char* e = getenv("OQPB_GRID_PCT")) ctx->grid_pct = std::max(10, atoi(e));
   if (const char* e = getenv("OQPB_TASK_CAP_LOG2")) ctx->task_cap = (size_t)1 << std::max(16, std::min(28, atoi(e)));
   // Rys tables
-  if (ctx->d_rys.ensure(sizeof(RYS_TAB_H)) != cudaSuccess) { delete ctx; return OQPB_ERR_CUDA; }
+  if (ctx->d_rys.ensure(sizeof(RYS_TAB_H) + sizeof(RYSF_TAB_H)) != cudaSuccess) { delete ctx; return OQPB_ERR_CUDA; }
   cudaMemcpy(ctx->d_rys.p, RYS_TAB_H, sizeof(RYS_TAB_H), cudaMemcpyHostToDevice);
+  cudaMemcpy(ctx->d_rys.as<double>() + RYS_NTAB, RYSF_TAB_H, sizeof(RYSF_TAB_H), cudaMemcpyHostToDevice);  // nroots 1, 2
   ctx->d_maxden.ensure(16);
   *out = ctx;
   return OQPB_OK;
@@ -1566,7 +1576,7 @@ int oqpb_rys(oqpb_ctx* ctx, int nroots, int npts, const double* x, double* t2, d
   CK(cudaMemcpy(dx.p, x, npts * sizeof(double), cudaMemcpyHostToDevice));
   EriArgs A;
   memset(&A, 0, sizeof A);
-  A.rys_tab = ctx->d_rys.as<double>() + RYS_OFF_H[nroots - 1];
+  A.rys_tab = rys_table(ctx, nroots);
   A.rys_xmax = RYS_XMAX_H[nroots - 1];
   for (int k = 0; k < 7; ++k) { A.herm_r[k] = RYS_HERM_R_H[nroots - 1][k]; A.herm_w[k] = RYS_HERM_W_H[nroots - 1][k]; }
   k_rys_test<<<(npts + 127) / 128, 128, 0, ctx->stream>>>(A, nroots, npts, dx.as<double>(), dt.as<double>(), dw.as<double>());
