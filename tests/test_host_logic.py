@@ -80,3 +80,23 @@ def test_two_rank_split_and_allreduce_gloo(tmp_path):
     outs = [p.communicate(timeout=300) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "OK" in outs[0][0]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU oracle timed on the host cores) prints one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra in ([], ["--cam"]):
+        out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c1", "--steps", "1",
+                              "--warmup", "0", "--cpu-seconds", "0.5"] + extra, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-500:]
+        lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        assert len(lines) == 1
+        d = json.loads(lines[0])
+        for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+            assert k in d, k
+        assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+        assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
