@@ -128,6 +128,28 @@ def cpu_sample(bs, d_packed, sx, target_s, nthreads=0, cam=False):
 
 MRSF_WORKLOADS = ("c5",)
 
+_SAVED_STDOUT = None
+
+
+def quiet_stdout():
+    """Multi-rank runs: libraries (NCCL prints its version line) must not write to stdout, which carries only the one JSON
+    line -- point fd 1 at stderr for the duration of the run and keep the real stdout for emit()."""
+    global _SAVED_STDOUT
+    if _SAVED_STDOUT is None:
+        sys.stdout.flush()
+        _SAVED_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    txt = json.dumps(line) + "\n"
+    if _SAVED_STDOUT is None:
+        sys.stdout.write(txt)
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_SAVED_STDOUT, txt.encode())
+
 
 def mrsf_cpu_sample(bs, d3, sx, target_s, nthreads=0):
     """Oracle int2_mrsf_data_t build (tdhf_mrsf_lib.F90:218-333) on a strided sample of the bra shell-pair list."""
@@ -162,7 +184,7 @@ def main_mrsf(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
+        quiet_stdout()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -281,7 +303,7 @@ def main_mrsf(args):
             r = mrsf_cpu_sample(bs, d3, sx, args.cpu_seconds)
             line["cpu_baseline"] = {"value": r["quartets"] / r["seconds"], "unit": "quartets/s", "cores": r["cores"], "kind": "port",
                                     "sample": f"every {r['stride']}-th bra shell pair, {r['quartets']} quartets in {r['seconds']:.1f} s"}
-        print(json.dumps(line))
+        emit(line)
     drv.clean()
     if world > 1:
         dist.destroy_process_group()
@@ -321,7 +343,7 @@ def run_reference(args):
                                        f"{quartets} quartets per {args.steps} steps"},
             "e2e": {"value": val, "unit": "quartets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -341,7 +363,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
+        quiet_stdout()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -483,7 +505,7 @@ def main():
             line["cpu_baseline"] = {"value": r["quartets"] / r["seconds"], "unit": "quartets/s", "cores": r["cores"], "kind": "port",
                                     "sample": f"every {r['stride']}-th bra shell pair of the cost-sorted list, "
                                               f"{r['quartets']} quartets in {r['seconds']:.1f} s"}
-        print(json.dumps(line))
+        emit(line)
     drv.clean()
     if world > 1:
         dist.destroy_process_group()
