@@ -1723,7 +1723,8 @@ struct GroupCfg {
   static constexpr int VL = C::NA * C::NB;
   static constexpr int NKET = C::NKET;
   static constexpr int acc_for(int g) { return ((VL + g - 1) / g) * NKET; }
-  static constexpr int LIMIT = OQPB_GRP_LIMIT;  // accumulators per lane for G < 32
+  // accumulators per lane for G < 32; (fs|dd) measured 27 % faster with 8 lanes x 72 accumulators than 16 x 36
+  static constexpr int LIMIT = (LA == 3 && LB == 0 && LC == 2 && LD == 2) ? 72 : OQPB_GRP_LIMIT;
   static constexpr int LIMIT32 = 72;    // ... and for full-warp groups
   static constexpr bool OK = (C::KS == 1) && acc_for(32) <= LIMIT32;
   static constexpr int G = acc_for(4) <= LIMIT ? 4 : (acc_for(8) <= LIMIT ? 8 : (acc_for(16) <= LIMIT ? 16 : 32));
