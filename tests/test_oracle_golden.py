@@ -208,3 +208,22 @@ def test_oracle_attenuated_integrals_closed_form(oracle_mod):
     assert np.abs(f0_ - f1_).max() < 1e-13
     qa = o.schwarz_attenuated(mu)
     assert (qa <= o.schwarz * (1 + 1e-12) + 1e-300).all() and qa.max() > 0
+
+
+def test_oracle_strided_partitions_sum_to_full(oracle_mod):
+    """The replicated-data split `mod(ij_pair, size) == rank` (int2.F90:759-761), which the bench's bounded CPU samples
+    and the multi-GPU partition rely on: strided partial builds of every consumer add up to the full build."""
+    bs = B.BasisSet(B.water_dimer(), "6-31g")
+    o = oracle_mod.Oracle(bs)
+    o.set_screening()
+    d = pack(decaying_density(bs))
+    full, st = o.fock(d, 0.5, 1.0, post=False)
+    parts = [o.fock(d, 0.5, 1.0, post=False, stride=3, offset=r) for r in range(3)]
+    assert np.abs(sum(p[0] for p in parts) - full).max() < 1e-12
+    assert sum(p[1]["nquartets"] for p in parts) == st["nquartets"] and sum(p[1]["nschwz"] for p in parts) == st["nschwz"]
+    rng = np.random.default_rng(2)
+    d3 = rng.normal(size=(2, 7, bs.nbf, bs.nbf)) * 0.1
+    f3, st3 = o.mrsf(d3, 0.5, 1.0)
+    p3 = [o.mrsf(d3, 0.5, 1.0, stride=2, offset=r) for r in range(2)]
+    assert np.abs(p3[0][0] + p3[1][0] - f3).max() < 1e-12
+    assert p3[0][1]["nquartets"] + p3[1][1]["nquartets"] == st3["nquartets"]
