@@ -1459,7 +1459,11 @@ __device__ __forceinline__ void rys_pair(const EriArgs& a, const double* __restr
   w = fma(s.t, e1, q[0].x - e2);
 }
 
-template <int LA, int LB, int LC, int LD, int PV, bool GS>
+// WPQ (warp per quartet): all 32 lanes work on ONE quartet and split its primitive quartets (ket primitives over
+// QS lanes x bra primitives over 32/QS lanes), the partial blocks are summed with shuffles and lane 0 carries on
+// alone.  Used for launches with few, heavily contracted quartets (small molecules), where one thread per quartet
+// would run thousands of primitive quartets serially while the rest of the GPU idles.
+template <int LA, int LB, int LC, int LD, int PV, bool GS, bool WPQ = false>
 __global__ void __launch_bounds__(GS ? MEDIUM_NT : SMALL_NT, GS ? min_ctas(MEDIUM_NT, OQPB_MED_REGS) : min_ctas(SMALL_NT, small_regcap<LA, LB, LC, LD>()))
 eri_small_kernel(const EriArgs A) {
   constexpr int NTH = GS ? MEDIUM_NT : SMALL_NT;
@@ -1480,16 +1484,18 @@ eri_small_kernel(const EriArgs A) {
   }
   const int lane = threadIdx.x & 31;
   // warp-uniform trip count: the digestion reduces across the lanes of a warp
-  for (unsigned tb = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); tb < ntasks; tb += gridDim.x * blockDim.x) {
-    const unsigned ti = tb + lane;
+  constexpr unsigned TPC = WPQ ? NTH / 32 : NTH;  // tasks per CTA and pass
+  for (unsigned tb = blockIdx.x * TPC + (WPQ ? (threadIdx.x >> 5) : (threadIdx.x & ~31u)); tb < ntasks; tb += gridDim.x * TPC) {
+    const unsigned ti = WPQ ? tb : tb + lane;
     const bool valid = ti < ntasks;
+    const bool validp = valid && (!WPQ || lane == 0);  // the lane that owns the finished block
     const int2 tk = A.tasks[valid ? ti : ntasks - 1];
     PairEntry pb = A.bra[tk.x], pk = A.ket[tk.y];
     if (!valid) pb.pcnt = pk.pcnt = 0;  // no primitive work, zero block
     // task of this lane's NEXT iteration: its pair entries are pulled towards the SM while this quartet is computed
     const unsigned tnext = ti + gridDim.x * blockDim.x;
     int2 tkn = make_int2(-1, -1);
-    if (tnext < ntasks) tkn = A.tasks[tnext];
+    if (!WPQ && tnext < ntasks) tkn = A.tasks[tnext];
     // density sub-blocks of matrix 0: issued now, consumed by the digestion after the primitive loop
     using Den = DenBlk<N0, N1, N2, N3>;
     constexpr bool DEN_BATCH = Den::SIZE + NTOT <= OQPB_DEN_BATCH_MAX;
@@ -1513,10 +1519,17 @@ eri_small_kernel(const EriArgs A) {
     // the L1 latency of these small dependent loads was 30 % of the stall samples of the contracted launches)
     const double2* pq0 = reinterpret_cast<const double2*>(A.prim + (size_t)pk.poff * PRIM_STRIDE);
     const double2* pp0 = reinterpret_cast<const double2*>(A.prim + (size_t)pb.poff * PRIM_STRIDE);
-    constexpr bool PIPE = prim_pipe<LA, LB, LC, LD>();
+    constexpr bool PIPE = prim_pipe<LA, LB, LC, LD>() && !WPQ;
+    // WPQ: lane = (lq, lp); ket primitives kq = lq, lq + QS, ...; bra primitives kp = lp, lp + 32/QS, ...
+    int kq0 = 0, kqs = 1, kp0 = 0, kps = 1;
+    if constexpr (WPQ) {
+      int qs = 1;
+      while (qs < 32 && qs < pk.pcnt) qs <<= 1;  // warp-uniform: all lanes hold the same quartet
+      kq0 = lane % qs; kqs = qs; kp0 = lane / qs; kps = 32 / qs;
+    }
     double2 nq01 = make_double2(0, 0), nq23 = nq01, nq45 = nq01;
     if (PIPE && pk.pcnt > 0) { nq01 = __ldg(pq0); nq23 = __ldg(pq0 + 1); nq45 = __ldg(pq0 + 2); }
-    for (int kq = 0; kq < pk.pcnt; ++kq) {
+    for (int kq = kq0; kq < pk.pcnt; kq += kqs) {
       if constexpr (!PIPE) { const double2* pq = pq0 + 3 * kq; nq01 = __ldg(pq); nq23 = __ldg(pq + 1); nq45 = __ldg(pq + 2); }
       const double2 q01 = nq01, q23 = nq23, q45 = nq45;
       if (PIPE && kq + 1 < pk.pcnt) {
@@ -1527,7 +1540,7 @@ eri_small_kernel(const EriArgs A) {
       if ((da0 * db) * (da0 * db) < thr) break;
       double2 np01 = make_double2(0, 0), np23 = np01, np45 = np01;
       if (PIPE && pb.pcnt > 0) { np01 = __ldg(pp0); np23 = __ldg(pp0 + 1); np45 = __ldg(pp0 + 2); }
-      for (int kp = 0; kp < pb.pcnt; ++kp) {
+      for (int kp = kp0; kp < pb.pcnt; kp += kps) {
         double2 p01 = np01, p23 = np23, p45 = np45;
         if constexpr (PIPE) {
           if (kp + 1 < pb.pcnt) {
@@ -1623,6 +1636,16 @@ eri_small_kernel(const EriArgs A) {
         }
       }
     }
+    if constexpr (WPQ) {
+      any = __any_sync(0xffffffffu, any);
+#pragma unroll
+      for (int e = 0; e < NCART4; ++e) {
+        double v = acc[e];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[e] = lane == 0 ? v : 0.0;
+      }
+    }
     if (tkn.x >= 0) {
       const char* nb_ = reinterpret_cast<const char*>(A.bra + tkn.x);
       const char* nk_ = reinterpret_cast<const char*>(A.ket + tkn.y);
@@ -1632,8 +1655,8 @@ eri_small_kernel(const EriArgs A) {
       asm volatile("prefetch.global.L1 [%0];" ::"l"(nk_ + 64));
     }
     if (A.mode != MODE_SYM && A.mode != MODE_GEN && !any) {  // (mode is uniform; SYM / GEN keep the warp together)
-      if (valid && A.mode == MODE_SCHWARZ) A.qout[tk.x] = 0.0;
-      if (valid && A.mode == MODE_BLOCK)
+      if (validp && A.mode == MODE_SCHWARZ) A.qout[tk.x] = 0.0;
+      if (validp && A.mode == MODE_BLOCK)
         for (int e = 0; e < NTOT; ++e) A.blockout[e] = 0.0;
       continue;
     }
@@ -1647,11 +1670,11 @@ eri_small_kernel(const EriArgs A) {
       double mx = 0.0;
 #pragma unroll
       for (int e = 0; e < NTOT; ++e) mx = fmax(mx, fabs(blk[e]));
-      if (valid) A.qout[tk.x] = sqrt(mx);
+      if (validp) A.qout[tk.x] = sqrt(mx);
       continue;
     }
     if (A.mode == MODE_BLOCK) {
-      if (valid) {
+      if (validp) {
 #pragma unroll
         for (int e = 0; e < NTOT; ++e) A.blockout[e] = blk[e];
       }
@@ -1674,9 +1697,9 @@ eri_small_kernel(const EriArgs A) {
     st_ints += (unsigned long long)nz * (unsigned)(8.0f * facf);
     if (A.mode == MODE_SYM) {
       // runs of equal bra / equal (bra, ket shell c) inside the warp; lanes without a quartet get unique keys
-      const long long kbra = valid ? (long long)tk.x : -1 - (long long)lane;
+      const long long kbra = validp ? (long long)tk.x : -1 - (long long)lane;
       const SegMask mbra = seg_make(kbra, lane);
-      const SegMask mc = seg_make(valid ? ((long long)tk.x << 20) | (long long)pk.sa : kbra, lane);
+      const SegMask mc = seg_make(validp ? ((long long)tk.x << 20) | (long long)pk.sa : kbra, lane);
       digest_sym_reg<N0, N1, N2, N3, !GS, DEN_BATCH>(A, blk, pb.oa, pb.ob, pk.oa, pk.ob, mbra, mc, den0, DEN_EARLY);
     } else {
       // MODE_GEN: the 32 blocks of the warp go to shared memory and are digested one after the other by all lanes
@@ -1684,7 +1707,7 @@ eri_small_kernel(const EriArgs A) {
       constexpr int GBS = NTOT | 1, SUB = gen_sub(NTOT, NTH / 32);
       double* wb = gsm + (GS ? 3 * NIJ1 * NKL1 * NTH : (RSM ? RysSmem<R>::doubles(A.rys_xmax) : 0)) +
                    (size_t)(threadIdx.x >> 5) * (SUB * GBS);
-      const unsigned live_all = __ballot_sync(0xffffffffu, valid && any);
+      const unsigned live_all = __ballot_sync(0xffffffffu, validp && any);
 #pragma unroll 1
       for (int h = 0; h < 32 / SUB; ++h) {
         unsigned live = live_all & (unsigned)(((1ull << SUB) - 1ull) << (h * SUB));
@@ -2165,6 +2188,33 @@ cudaError_t launch_eri(const EriArgs& args, int nblocks, cudaStream_t st) {
   }
 }
 
+// warp-per-quartet launch of the register kernel (classes with <= SMALL_MAX Cartesian integrals); nullptr otherwise
+template <int LA, int LB, int LC, int LD, int PV>
+cudaError_t launch_eri_wpq(const EriArgs& args, int nblocks, cudaStream_t st) {
+  using Cfg = ClassCfg<LA, LB, LC, LD>;
+  if constexpr (Cfg::NCART4 <= SMALL_MAX) {
+    constexpr int R = Cfg::R;
+    constexpr int NTOT = Shell<LA, PV>::NOUT * Shell<LB, PV>::NOUT * Shell<LC, PV>::NOUT * Shell<LD, PV>::NOUT;
+    constexpr size_t gen = (size_t)(SMALL_NT / 32) * (gen_sub(NTOT, SMALL_NT / 32) * (NTOT | 1) + 2 * gen_sub(NTOT, SMALL_NT / 32)) * sizeof(double);
+    const size_t smem = (RysSmem<R>::USE ? (size_t)RysSmem<R>::doubles(args.rys_xmax) * sizeof(double) : 0) +
+                        (args.mode == MODE_GEN ? gen : 0);
+    static DevFlags flags;
+    bool& attr_set = flags.cur();
+    if (!attr_set && smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(eri_small_kernel<LA, LB, LC, LD, PV, false, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    eri_small_kernel<LA, LB, LC, LD, PV, false, true><<<nblocks, SMALL_NT, smem, st>>>(args);
+    return cudaGetLastError();
+  } else {
+    return cudaErrorNotSupported;
+  }
+}
+template <int LA, int LB, int LC, int LD>
+constexpr bool class_has_wpq() { return ClassCfg<LA, LB, LC, LD>::NCART4 <= SMALL_MAX; }
+
 template <int LA, int LB, int LC, int LD>
 constexpr int class_tasks_per_cta() {
   using C = ClassCfg<LA, LB, LC, LD>;
@@ -2180,7 +2230,7 @@ constexpr int class_max_ctas() {
 }
 
 using LaunchFn = cudaError_t (*)(const EriArgs&, int, cudaStream_t);
-struct ClassEntry { LaunchFn launch; int qpb; int nt; size_t smem; int maxcta; };
+struct ClassEntry { LaunchFn launch; int qpb; int nt; size_t smem; int maxcta; LaunchFn launch_wpq; };
 // class table: [pure variant PV = (d pure) | (f pure) << 1][quartet class]
 const ClassEntry* class_table(int pv);
 

@@ -166,6 +166,7 @@ struct oqpb_ctx {
   cudaEvent_t lane_ev[NSTREAM] = {};
   int nlanes = 4;      // OQPB_NLANES
   int grid_pct = 100;  // OQPB_GRID_PCT: scales the per-class grid caps
+  size_t wpq_max_tasks = 16384;  // OQPB_WPQ_MAX: largest launch (candidate quartets) that uses the warp-per-quartet kernels
   cudaEvent_t fork_ev = nullptr;
   size_t task_cap = (size_t)1 << 23;
   int rank = 0, nranks = 1;
@@ -886,10 +887,13 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     A.gen_mcount = S.gen_mcount >= 0 ? S.gen_mcount : S.gen_nm;
     const int qcls = quartet_class(pc_of(ch.pca), pc_of(ch.pcb));
     const ClassEntry& ce = tab[qcls];
-    size_t nb = std::min<size_t>((ch.cand + ce.qpb - 1) / ce.qpb, (size_t)ce.maxcta * ctx->grid_pct / 100);
+    // few, heavily contracted quartets (small molecules): warp per quartet, lanes over the primitive quartets
+    const bool wpq = ce.launch_wpq != nullptr && ch.cand <= ctx->wpq_max_tasks && (ch.pca % NBK >= 2 || ch.pcb % NBK >= 2);
+    const size_t tasks_per_cta = wpq ? 4 : (size_t)ce.qpb;
+    size_t nb = std::min<size_t>((ch.cand + tasks_per_cta - 1) / tasks_per_cta, (size_t)ce.maxcta * ctx->grid_pct / 100);
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (ctx->profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, cs); }
-    CK(ce.launch(A, (int)std::max<size_t>(nb, 1), cs));
+    CK((wpq ? ce.launch_wpq : ce.launch)(A, (int)std::max<size_t>(nb, 1), cs));
     if (ctx->profile) {
       cudaEventRecord(pe1, cs);
       cudaEventSynchronize(pe1);
@@ -1003,6 +1007,7 @@ int oqpb_ctx_create(oqpb_ctx** out, int device) {
   // tuning knobs (tools/sweep_knobs.sh)
   if (const char* e = getenv("OQPB_NLANES")) ctx->nlanes = std::max(1, std::min((int)oqpb_ctx::NSTREAM, atoi(e)));
   if (const char* e = getenv("OQPB_GRID_PCT")) ctx->grid_pct = std::max(10, atoi(e));
+  if (const char* e = getenv("OQPB_WPQ_MAX")) ctx->wpq_max_tasks = (size_t)std::max(0, atoi(e));
   if (const char* e = getenv("OQPB_TASK_CAP_LOG2")) ctx->task_cap = (size_t)1 << std::max(16, std::min(28, atoi(e)));
   // Rys tables
   if (ctx->d_rys.ensure(sizeof(RYS_TAB_H) + sizeof(RYSF_TAB_H)) != cudaSuccess) { delete ctx; return OQPB_ERR_CUDA; }
