@@ -55,6 +55,18 @@ module oqp_b200_shim
       real(c_double), intent(in) :: d3(*); real(c_double), intent(out) :: f3(*)
       real(c_double), value :: se, sc; integer(c_long_long), intent(out) :: nskipped
     end function
+    integer(c_int) function oqpb_jk_td_cam(ctx, d2, nvec, flags, alpha, beta, mu, alpha_coulomb, beta_coulomb, apb, amb, &
+                                           nskipped) bind(C, name="oqpb_jk_td_cam")
+      import; type(c_ptr), value :: ctx; integer(c_int), value :: nvec, flags
+      real(c_double), intent(in) :: d2(*); real(c_double), intent(out) :: apb(*), amb(*)
+      real(c_double), value :: alpha, beta, mu, alpha_coulomb, beta_coulomb; integer(c_long_long), intent(out) :: nskipped
+    end function
+    integer(c_int) function oqpb_jk_mrsf_cam(ctx, d3, nvec, ncomp, alpha, beta, mu, alpha_coulomb, f3, nskipped) &
+        bind(C, name="oqpb_jk_mrsf_cam")
+      import; type(c_ptr), value :: ctx; integer(c_int), value :: nvec, ncomp
+      real(c_double), intent(in) :: d3(*); real(c_double), intent(out) :: f3(*)
+      real(c_double), value :: alpha, beta, mu, alpha_coulomb; integer(c_long_long), intent(out) :: nskipped
+    end function
     !> device-resident variant (d3_dev, f3_dev = CUDA device pointers, e.g. from a routec_sig session)
     integer(c_int) function oqpb_jk_mrsf_dev(ctx, d3_dev, nvec, ncomp, se, sc, f3_dev) bind(C, name="oqpb_jk_mrsf_dev")
       import; type(c_ptr), value :: ctx, d3_dev, f3_dev; integer(c_int), value :: nvec, ncomp
@@ -76,6 +88,7 @@ module oqp_b200_shim
     procedure :: run_fock_cam => shim_run_fock_cam  !< same consumers through int2_run_cam (int2.F90:538-584)
     procedure :: run_td => shim_run_td          !< int2_td_data_t
     procedure :: run_mrsf => shim_run_mrsf      !< int2_mrsf_data_t
+    procedure :: run_mrsf_cam => shim_run_mrsf_cam  !< int2_mrsf_data_t through int2_run_cam (pass 2: component 7 exchange)
     procedure :: clean => shim_clean
   end type
 
@@ -178,6 +191,18 @@ contains
     integer, intent(out) :: info
     integer(c_long_long) :: ns
     info = oqpb_jk_mrsf(this%ctx, d3, int(size(d3, 1), c_int), int(size(d3, 2), c_int), se, sc, f3, ns)
+    if (info == 0) this%skipped = int(ns)
+  end subroutine
+
+  !> run(int2_data, cam=.true., alpha, beta, mu[, alpha_coulomb]) with the MRSF consumer (tdhf_mrsf_lib.F90:279-326)
+  subroutine shim_run_mrsf_cam(this, d3, alpha, beta, mu, alpha_coulomb, f3, info)
+    class(oqpb_int2_t), intent(inout) :: this
+    real(dp), contiguous, intent(in) :: d3(:,:,:,:)
+    real(dp), intent(in) :: alpha, beta, mu, alpha_coulomb
+    real(dp), contiguous, intent(out) :: f3(:,:,:,:)
+    integer, intent(out) :: info
+    integer(c_long_long) :: ns
+    info = oqpb_jk_mrsf_cam(this%ctx, d3, int(size(d3, 1), c_int), int(size(d3, 2), c_int), alpha, beta, mu, alpha_coulomb, f3, ns)
     if (info == 0) this%skipped = int(ns)
   end subroutine
 
