@@ -33,6 +33,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cam", action="store_true", help="range-separated two-pass build (CAM-B3LYP: alpha 0.19, beta 0.46, mu 0.33)")
+    ap.add_argument("--cutoff", type=float, default=5e-11, help="integral cutoff (MRSF workloads; the reference's response default is 1e-8, types.F90:185)")
     ap.add_argument("--nvec", type=int, default=12, help="MRSF workloads (c5): Davidson trial vectors per build (x 7 densities)")
     return ap.parse_args()
 
@@ -82,6 +83,36 @@ class ClockSampler:
         return out
 
 
+def host_threads():
+    """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must not
+    inherit that (a 1-thread reference would inflate every N > 1 ratio), so the oracle is given an explicit count."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def workload_config(args, bs, W, sx, nvec=None):
+    """The keys that identify the workload: identical in the `ours` and `reference` arms."""
+    cfg = {"workload": W.WORKLOADS.get(args.workload, args.workload), "nshell": int(bs.nshell), "nbf": int(bs.nbf),
+           "cutoff": 5e-11, "scale_exchange": sx,
+           "density": ("synthetic general (non-symmetric) decaying, seed 7" if nvec else "synthetic decaying, seed 7"),
+           "cam": dict(CAM, passes=2) if args.cam else None}
+    if nvec:
+        cfg.update({"nvec": nvec, "densities": nvec * 7})
+    return cfg
+
+
+def dram_traffic(workload):
+    """HBM bytes per build summed over the ERI launches, from the committed ncu pass
+    (profiles/r02_dram_<workload>.json, written by tools/dram_traffic.py on the GPU box); None when not captured."""
+    p = os.path.join(ROOT, "profiles", f"r02_dram_{workload}.json")
+    try:
+        return json.load(open(p))["dram_bytes_per_build"]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -96,6 +127,7 @@ CAM = {"alpha": 0.19, "beta": 0.46, "mu": 0.33}  # CAM-B3LYP
 
 
 def cpu_sample(bs, d_packed, sx, target_s, nthreads=0, cam=False):
+    nthreads = nthreads or host_threads()
     """Oracle (C++/OpenMP restatement of int2_twoei, the reference's OpenMP CPU path) on a bounded,
     strided sample of the cost-sorted bra shell-pair list of the SAME workload."""
     from oracle.oracle import Oracle, max_threads
@@ -123,7 +155,7 @@ def cpu_sample(bs, d_packed, sx, target_s, nthreads=0, cam=False):
         st = build(stride2)
         dt = time.perf_counter() - t
         stride = stride2
-    return {"quartets": st["nquartets"], "seconds": dt, "stride": stride, "cores": max_threads() if nthreads == 0 else nthreads}
+    return {"quartets": st["nquartets"], "seconds": dt, "stride": stride, "cores": nthreads}
 
 
 MRSF_WORKLOADS = ("c5",)
@@ -151,10 +183,11 @@ def emit(line: dict):
         os.write(_SAVED_STDOUT, txt.encode())
 
 
-def mrsf_cpu_sample(bs, d3, sx, target_s, nthreads=0):
+def mrsf_cpu_sample(bs, d3, sx, target_s, nthreads=0, cutoff=5e-11):
+    nthreads = nthreads or host_threads()
     """Oracle int2_mrsf_data_t build (tdhf_mrsf_lib.F90:218-333) on a strided sample of the bra shell-pair list."""
-    from oracle.oracle import Oracle, max_threads
-    o = Oracle(bs)
+    from oracle.oracle import Oracle
+    o = Oracle(bs, cutoff)
     o.set_screening()
     npair = bs.nshell * (bs.nshell + 1) // 2
     stride = max(1, npair // 200)
@@ -167,7 +200,7 @@ def mrsf_cpu_sample(bs, d3, sx, target_s, nthreads=0):
         _, st = o.mrsf(d3, sx, 1.0, nthreads=nthreads, stride=stride2, offset=1 % stride2)
         dt = time.perf_counter() - t
         stride = stride2
-    return {"quartets": st["nquartets"], "seconds": dt, "stride": stride, "cores": max_threads() if nthreads == 0 else nthreads}
+    return {"quartets": st["nquartets"], "seconds": dt, "stride": stride, "cores": nthreads}
 
 
 def main_mrsf(args):
@@ -192,7 +225,7 @@ def main_mrsf(args):
     nvec, ncomp, sx = args.nvec, 7, 0.5  # BHHLYP: 50 % exact exchange
     d3 = W.mrsf_densities(bs, nvec, ncomp)
     d3f = np.ascontiguousarray(np.transpose(d3, (3, 2, 1, 0)))  # Fortran d3(v, c, mu, nu), v fastest
-    drv = Int2Compute(local).init(bs)
+    drv = Int2Compute(local).init(bs, args.cutoff)
     t0 = time.perf_counter()
     drv.set_screening()
     t_screen = time.perf_counter() - t0
@@ -283,14 +316,12 @@ def main_mrsf(args):
             "metric": "shell_quartets_per_s", "value": nq_step / (ms_per_step * 1e-3), "unit": "quartets/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": W.WORKLOADS.get(args.workload, args.workload), "nshell": bs.nshell, "nbf": bs.nbf,
-                       "cutoff": 5e-11, "scale_exchange": sx, "nvec": nvec, "densities": nvec * ncomp,
-                       "density": "synthetic general (non-symmetric) decaying, seed 7", "quartets_per_build": nq_step,
-                       "mrsf_builds_per_s": 1e3 / ms_per_step, "l2": "flushed between steps (256 MB fill)",
-                       "schwarz_setup_s": t_screen,
+            "config": dict(workload_config(args, bs, W, sx, nvec), cutoff=args.cutoff),
+            "detail": {"quartets_per_build": nq_step, "mrsf_builds_per_s": 1e3 / ms_per_step,
+                       "l2": "flushed between steps (256 MB fill)", "schwarz_setup_s": t_screen,
                        "parallelism": f"bra shell pairs cyclic over {world} GPU(s), 1 NCCL all-reduce of f3"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": dram_traffic(args.workload),
                          "kernel": "eri_*_kernel family, MODE_GEN: Rys ERI + DMMA m8n8k4 multi-density digestion",
                          "peak_source": "FP64 FMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "algorithmic_flops_per_step": flops_all / args.steps, "kernel_ms_per_step": kernel_ms / args.steps,
@@ -300,7 +331,7 @@ def main_mrsf(args):
             "gpu_launches": launches, "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
-            r = mrsf_cpu_sample(bs, d3, sx, args.cpu_seconds)
+            r = mrsf_cpu_sample(bs, d3, sx, args.cpu_seconds, cutoff=args.cutoff)
             line["cpu_baseline"] = {"value": r["quartets"] / r["seconds"], "unit": "quartets/s", "cores": r["cores"], "kind": "port",
                                     "sample": f"every {r['stride']}-th bra shell pair, {r['quartets']} quartets in {r['seconds']:.1f} s"}
         emit(line)
@@ -319,15 +350,16 @@ def run_reference(args):
     mol, bs = W.build(args.workload)
     sx = W.scale_exchange(args.workload)
     if args.workload in MRSF_WORKLOADS:
+        sx = 0.5  # BHHLYP, as in main_mrsf
         dp = W.mrsf_densities(bs, args.nvec)
-        sampler = mrsf_cpu_sample
+        sampler = lambda *a, **k: mrsf_cpu_sample(*a, cutoff=args.cutoff, **k)
     else:
         from openqp_b200.scf import pack
         dp = pack(W.synthetic_density(bs))
         sampler = cpu_sample
     times, quartets, stride, cores = [], 0, 1, 1
     for it in range(args.warmup + args.steps):
-        kw = {"cam": True} if (args.cam and sampler is cpu_sample) else {}
+        kw = {"cam": True} if (args.cam and args.workload not in MRSF_WORKLOADS) else {}
         r = sampler(bs, dp, sx, args.cpu_seconds if it >= args.warmup else min(args.cpu_seconds, 3.0), **kw)
         if it >= args.warmup:
             times.append(r["seconds"]); quartets += r["quartets"]; stride = r["stride"]; cores = r["cores"]
@@ -336,9 +368,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "shell_quartets_per_s", "value": val, "unit": "quartets/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / max(args.steps, 1),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": W.WORKLOADS.get(args.workload, args.workload), "nshell": bs.nshell, "nbf": bs.nbf,
-                       "cutoff": 5e-11, "density": "synthetic decaying, seed 7"},
+            "config": (dict(workload_config(args, bs, W, sx, args.nvec), cutoff=args.cutoff) if args.workload in MRSF_WORKLOADS
+                       else workload_config(args, bs, W, sx)),
             "cpu_baseline": {"value": val, "unit": "quartets/s", "cores": cores, "kind": "port",
+                             "note": "Rys-only C++/OpenMP port of int2_twoei; stock OpenQP (rotated-axis + libint) is faster",
                              "sample": f"every {stride}-th bra shell pair of the cost-sorted list (int2.F90:864-921), "
                                        f"{quartets} quartets per {args.steps} steps"},
             "e2e": {"value": val, "unit": "quartets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -387,13 +420,21 @@ def main():
     if args.cam:
         drv.set_screening_cam(CAM["mu"])  # attenuated Schwarz matrix: once per geometry, like set_screening
 
-    def step_dev():
+    ar_events = []
+
+    def step_dev(timed=False):
         if args.cam:
             drv.fock_cam_dev(d_dev.data_ptr(), f_dev.data_ptr(), 1, CAM["alpha"], CAM["beta"], CAM["mu"])
         else:
             drv.fock_dev(d_dev.data_ptr(), f_dev.data_ptr(), 1, scale_exchange=sx)
         if world > 1:
+            if timed:
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record(stream)
             dist.all_reduce(f_dev)
+            if timed:
+                a1.record(stream)
+                ar_events.append((a0, a1))
         drv.fock_post_dev(f_dev.data_ptr(), 1)
 
     def barrier():
@@ -416,16 +457,24 @@ def main():
         flush.fill_(1.0)
         barrier()
         ev0.record(stream)
-        step_dev()
+        step_dev(timed=True)
         ev1.record(stream)
         barrier()
         tot_ms += ev0.elapsed_time(ev1)
         st = drv.last_stats()
         kernel_ms += st["kernel_ms"]; flops += st["flops"]; nq += st["nquartets"]; launches += st["launches"] + 8
-    t = torch.tensor([tot_ms, float(nq), flops, kernel_ms], dtype=torch.float64, device=dev)
+    ar_ms = sum(a0.elapsed_time(a1) for a0, a1 in ar_events)
+    t = torch.tensor([tot_ms, float(nq), flops, kernel_ms, ar_ms], dtype=torch.float64, device=dev)
+    rank_stats = None
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        tmin = t.clone(); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        # per-rank ERI kernel time (imbalance) and the all-reduce as seen by the fastest rank (the slowest rank's
+        # all-reduce time is the collective itself, the others' includes the wait for it)
+        rank_stats = {"kernel_ms_min": float(tmin[3]) / args.steps, "kernel_ms_mean": float(tsum[3]) / world / args.steps,
+                      "kernel_ms_max": float(tmax[3]) / args.steps, "allreduce_ms": float(tmin[4]) / args.steps,
+                      "allreduce_plus_wait_ms_max": float(tmax[4]) / args.steps}
         tot_ms, kernel_ms = float(tmax[0]), float(tmax[3])
         nq_all, flops_all = float(tsum[1]), float(tsum[2])
     else:
@@ -483,14 +532,14 @@ def main():
             "metric": "shell_quartets_per_s", "value": value, "unit": "quartets/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": W.WORKLOADS.get(args.workload, args.workload), "nshell": bs.nshell, "nbf": bs.nbf,
-                       "cutoff": 5e-11, "scale_exchange": sx, "density": "synthetic decaying, seed 7",
-                       "cam": dict(CAM, passes=2) if args.cam else None,
-                       "quartets_per_build": nq_step, "fock_builds_per_s": 1e3 / ms_per_step,
-                       "l2": "flushed between steps (256 MB fill)", "schwarz_setup_s": t_screen,
+            "config": workload_config(args, bs, W, sx),
+            "detail": {"quartets_per_build": nq_step, "fock_builds_per_s": 1e3 / ms_per_step,
+                       "l2": "flushed between steps (256 MB fill)", "schwarz_setup_s": t_screen, "ranks": rank_stats,
                        "parallelism": f"bra shell pairs cyclic over {world} GPU(s), 1 NCCL all-reduce of the packed Fock"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": dram_traffic(args.workload),
+                         "traffic_note": "HBM bytes per build over all ERI launches (ncu dram__bytes_read+write, profiles/); "
+                                         "algorithmic bytes = 16 ntri + pair table, the bound is FP64",
                          "kernel": "eri_kernel<la,lb,lc,ld> family (Rys ERI + fused J/K digestion), per-GPU average",
                          "peak_source": "FP64 FMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "algorithmic_flops_per_step": flops_all / args.steps, "kernel_ms_per_step": kernel_ms / args.steps,
@@ -504,7 +553,9 @@ def main():
             r = cpu_sample(bs, d, sx, args.cpu_seconds, cam=args.cam)
             line["cpu_baseline"] = {"value": r["quartets"] / r["seconds"], "unit": "quartets/s", "cores": r["cores"], "kind": "port",
                                     "sample": f"every {r['stride']}-th bra shell pair of the cost-sorted list, "
-                                              f"{r['quartets']} quartets in {r['seconds']:.1f} s"}
+                                              f"{r['quartets']} quartets in {r['seconds']:.1f} s",
+                                    "note": "Rys-only C++/OpenMP port of int2_twoei (general Rys roots for every nroots); "
+                                            "stock OpenQP uses rotated-axis s/p/d code and libint for f and is faster"}
         emit(line)
     drv.clean()
     if world > 1:

@@ -39,6 +39,15 @@ enum { OQPB_TD_APB = 1, OQPB_TD_AMB = 2, OQPB_TD_TDA = 4, OQPB_TD_TDA_COULOMB = 
 
 /* ---- lifetime: replaces int2_compute_t construction/clean (int2.F90:137-185, 245-289) ------------- */
 int  oqpb_ctx_create(oqpb_ctx** ctx, int device);
+/* One context over ndev GPUs of this node, driven from a single process (devices == NULL: 0 .. ndev-1): basis, pair
+ * table, Schwarz matrix and densities are replicated, the bra shell-pair list is split over the devices (on top of
+ * oqpb_set_partition's rank split), and the partial results are summed by ONE ncclAllReduce(ncclDouble, ncclSum) on
+ * the compute streams -- the replacement of `pe%allreduce` at the end of int2_twoei (int2.F90:1392-1397,
+ * parallel.F90:429-440).  A non-MPI OpenQP (ENABLE_MPI is OFF by default, CMakeLists.txt:76) reaches every GPU of the
+ * box this way: oqpb_fock, oqpb_fock_cam, oqpb_jk_mrsf[_cam] and routec_fock_jk use all members; oqpb_jk_td runs on the
+ * first device.  The *_dev entries act on the first device's slice only.  NCCL (libnccl.so.2) is loaded on demand.   */
+int  oqpb_ctx_create_multi(oqpb_ctx** ctx, int ndev, const int* devices);
+int  oqpb_ctx_ndevices(const oqpb_ctx* ctx);
 void oqpb_ctx_destroy(oqpb_ctx* ctx);
 const char* oqpb_last_error(const oqpb_ctx* ctx);
 
@@ -60,10 +69,18 @@ int oqpb_set_cutoff(oqpb_ctx* ctx, double cutoff);
 int oqpb_set_screening(oqpb_ctx* ctx, const double* schwarz_in);
 int oqpb_get_schwarz(oqpb_ctx* ctx, double* schwarz_out /* nshell*nshell */);
 
-/* Multi-GPU / MPI replicated-data split of the bra shell-pair list, the reference's
- * `mod(ij_pair, size) == rank` (int2.F90:759-761).  The caller sums the partial results
- * (pe%allreduce, int2.F90:1396; NCCL all-reduce on the *_dev entry points).                           */
+/* Multi-GPU / MPI replicated-data split of the work, the role of the reference's `mod(ij_pair, size) == rank`
+ * (int2.F90:759-761): the bras of every pair list (angular-momentum class x contraction bucket, Schwarz-sorted) are
+ * dealt cyclically, p % nranks == rank inside each list, so every rank gets the same class mix.  A rank's slice (and
+ * its nskipped) therefore differs from the slice a native OpenQP rank would take: all ranks of a job must use this
+ * library.  The caller sums the partial results (pe%allreduce, int2.F90:1396) -- or uses a multi-device context.     */
 int oqpb_set_partition(oqpb_ctx* ctx, int rank, int nranks);
+
+/* Test hook: restrict the following builds to the quartets whose reference bra pair (the canonically larger
+ * shell pair, the `ij_pair` of int2.F90:756-780) is flagged in mask[i(i+1)/2+j] (0-based, i >= j, npairs =
+ * nshell(nshell+1)/2 bytes); NULL lifts the restriction.  Lets a strided sample of a large build be compared
+ * with the CPU oracle run on the same bra subset (the oracle's stride/offset over its cost-sorted list).   */
+int oqpb_set_bra_mask(oqpb_ctx* ctx, const unsigned char* mask, long long npairs);
 
 /* fock_jk (scf_addons.F90:1063-1214) = int2_rhf_data_t / int2_urohf_data_t consumers
  * (int2.F90:1414-1578) + 0.5/diagonal post-scaling (:1177-1185) when `post` != 0:
@@ -72,8 +89,9 @@ int oqpb_set_partition(oqpb_ctx* ctx, int rank, int nranks);
  * d, f: packed (ntri, nfocks).  nskipped = int2_compute_t%skipped (nschwz).  Host pointers.           */
 int oqpb_fock(oqpb_ctx* ctx, int urohf, const double* d, double* f, int nfocks, double scale_exchange,
               double scale_coulomb, int post, long long* nskipped);
-/* same with DEVICE pointers, asynchronous on the ctx stream, no host copies: the result stays in HBM
- * for the caller's NCCL all-reduce; oqpb_fock_post_dev applies the 0.5/diag scaling afterwards.       */
+/* same with DEVICE pointers, no host copies: the result stays in HBM for the caller's NCCL all-reduce;
+ * oqpb_fock_post_dev applies the 0.5/diag scaling afterwards.  The kernels run on the ctx stream (and its helper
+ * streams, joined back into it), but the call BLOCKS the host until the build's statistics are back.               */
 int oqpb_fock_dev(oqpb_ctx* ctx, int urohf, const double* d_dev, double* f_dev, int nfocks,
                   double scale_exchange, double scale_coulomb);
 int oqpb_fock_post_dev(oqpb_ctx* ctx, double* f_dev, int nfocks);
@@ -110,6 +128,29 @@ int oqpb_jk_mrsf(oqpb_ctx* ctx, const double* d3, int nvec, int ncomp, double sc
  * routec_sig_iter, routec_sig.F90:28-56, would sit on this entry).                                     */
 int oqpb_jk_mrsf_dev(oqpb_ctx* ctx, const double* d3_dev, int nvec, int ncomp, double scale_exchange,
                      double scale_coulomb, double* f3_dev);
+
+/* Generic J/K for n general (non-symmetric) AO matrices P (nbf, nbf, n), column-major:
+ *   J_m(a,b) = sum_cd (ab|cd) P_m(c,d)  when want_j[m];   K_m(a,c) = sum_bd (ab|cd) P_m(b,d)  when want_k[m]
+ * screened with max|P_m| per shell block over all m (shltd, tdhf_lib.F90:300-325).  J, K: (nbf, nbf, n); slabs that were
+ * not asked for are left untouched.  Every J/K consumer of the reference is a linear combination of these; the Z-vector and
+ * gradient drivers (modules/tdhf_mrsf_z_vector.F90, tdhf_sf_z_vector.F90, tdhf_z_vector.F90) can call it directly.        */
+int oqpb_jk(oqpb_ctx* ctx, int n, const double* P, const int* want_j, const int* want_k, double* J, double* K,
+            long long* nskipped);
+/* int2_tdgrd_data_t (tdhf_lib.F90:33-36, update :228-295): two spin blocks d2(nbf,nbf,2); flags = OQPB_TD_APB | OQPB_TD_AMB.
+ *   apb(:,:,s) = 2 sc J[P_1+P_2] - se K[P_s+P_s^T] (symmetrised as parallel_stop does), amb(:,:,1) = se K[P_1^T-P_1], amb(:,:,2) = 0 */
+int oqpb_jk_tdgrd(oqpb_ctx* ctx, const double* d2, int flags, double scale_exchange, double scale_coulomb, double* apb,
+                  double* amb, long long* nskipped);
+/* int2_rpagrd_data_t (tdhf_lib.F90:42-57, 1068-1320): xpy, xmy, t (nbf, nbf, nspin, np | nm | nt) -> hpp = H+[X+Y],
+ * hpt = H+[T] (both symmetrised, :1138-1141), hmm = H-[X-Y].  X+Y and T must be symmetric matrices (they are at every call
+ * site: the reference's update reads one triangle of them).  Pointers may be NULL when the count is 0.                   */
+int oqpb_jk_rpagrd(oqpb_ctx* ctx, int nspin, int np, int nm, int nt, const double* xpy, const double* xmy, const double* t,
+                   double scale_exchange, double scale_coulomb, double* hpp, double* hpt, double* hmm, long long* nskipped);
+/* int2_umrsf_data_t (tdhf_mrsf_lib.F90:28-32, update :337-426): d3, f3 (nvec, 11, nbf, nbf), nvec fastest; the _cam variant
+ * is int2_run_cam (pass 2 = attenuated exchange of component 11 only).                                                  */
+int oqpb_jk_umrsf(oqpb_ctx* ctx, const double* d3, int nvec, double scale_exchange, double scale_coulomb, double* f3,
+                  long long* nskipped);
+int oqpb_jk_umrsf_cam(oqpb_ctx* ctx, const double* d3, int nvec, double alpha, double beta, double mu, double alpha_coulomb,
+                      double* f3, long long* nskipped);
 
 /* The response consumers through int2_run_cam (range-separated functionals):
  *   TD   (tdhf_lib.F90:140-224): the same update in both passes, pass 2 with Erf-attenuated integrals and

@@ -22,7 +22,9 @@
 // mu2inv != 0 selects Erf-attenuated integrals (CAM second pass).
 #pragma once
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <type_traits>
 #include <utility>
 
@@ -53,6 +55,9 @@
 #endif
 #ifndef OQPB_GRP_LIMIT
 #define OQPB_GRP_LIMIT 56
+#endif
+#ifndef OQPB_RUN_M
+#define OQPB_RUN_M 7
 #endif
 #ifndef OQPB_REGVRR_MAX
 #define OQPB_REGVRR_MAX 64
@@ -95,7 +100,12 @@ struct EriArgs {
   const int* aooff;
   const int2* tasks;
   const unsigned* ntasks;  // device-resident count
+  unsigned task_cap;       // capacity of `tasks` (0 = unbounded): k_enum counts past it, the kernels must not read past it
   unsigned* counter;       // dynamic task fetch
+  // run kernels (eri_run_kernel): warp work items = up to RUN_LEN consecutive surviving kets of ONE bra, written by k_enum
+  const int2* items;       // x = bra entry | length << 24, y = first task index
+  const unsigned* nitems;
+  unsigned item_cap;
   const double* rys_tab;   // table base for this nroots
   int rys_xmax;
   double herm_r[7], herm_w[7];
@@ -119,6 +129,8 @@ struct EriArgs {
   int gen_nmat_total;  // nmat for interleaved layout (may exceed MAX_MATS): the stride between AO pairs
   int gen_mcount;      // matrices that take the exchange part, starting at Pgen / Fgen (<= gen_nmat_total; the CAM second
                        // pass of the MRSF consumer passes Pgen + 6 nvec and nvec: component 7 only)
+  int gen_xoff;        // first matrix that takes the exchange part (matrices [gen_xoff, gen_xoff + gen_mcount)); the generic
+                       // J/K entry keeps Coulomb-only matrices in front of it
   int gen_ncoul;       // interleaved: component index < gen_ncoul gets Coulomb (uses comp = m / nvec ... see kernel)
   int gen_nvec;
   const double* Pgen;  // interleaved density
@@ -212,7 +224,8 @@ struct QInfo {  // 64 ints per quartet in shared memory
 
 // ---------------------------------------------------------------------------------------------------
 // roots / weights for function f (f < R: root t^2, f >= R: weight) at X
-// Table format per nroots: unit X intervals with 12-term Chebyshev fits; nroots = 1 ((ss|ss), (ps|ss): the most
+// Table format per nroots: unit X intervals with 12-term polynomial fits (Chebyshev fits of tools/gen_rys_tables.py,
+// converted to monomial coefficients in t in [-1, 1] when the context is created); nroots = 1 ((ss|ss), (ps|ss): the most
 // heavily contracted classes, where the interpolation is a third of the FP64 work) uses quarter-width intervals with
 // 8 terms (tools/gen_rys_tables_fine.py, fit error < 2e-15): -4 % on those classes.  The same format for nroots = 2
 // was measured slower: its 51 KB table per CTA eats the L1 of the 128-register classes.
@@ -234,15 +247,12 @@ __device__ __forceinline__ double rys_eval(const EriArgs& a, double X, int f) {
   int iv = (int)xs;
   double t = 2.0 * (xs - (double)iv) - 1.0;
   const double* c = a.rys_tab + ((size_t)iv * (2 * R) + f) * NCF;
-  // Clenshaw
-  double b1 = 0.0, b2 = 0.0, t2 = 2.0 * t;
+  // Horner on the monomial coefficients (converted from the Chebyshev fits at context creation, oqp_b200.cu
+  // cheb_to_monomial): one DFMA per term instead of the DADD + DFMA of a Clenshaw step, same accuracy (2.3e-16 rel.)
+  double b = __ldg(c + NCF - 1);
 #pragma unroll
-  for (int k = NCF - 1; k >= 1; --k) {
-    double b0 = fma(t2, b1, __ldg(c + k) - b2);
-    b2 = b1;
-    b1 = b0;
-  }
-  return fma(t, b1, __ldg(c) - b2);
+  for (int k = NCF - 2; k >= 0; --k) b = fma(b, t, __ldg(c + k));
+  return b;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -808,7 +818,7 @@ __device__ __forceinline__ void digest_gen(const EriArgs& A, const double* blk, 
   }
   if (ck != 0.0) {
     for (int e = t; e < n0 * n2 * MC; e += ts) {  // (a,c)
-      int m = e % MC, o = e / MC;
+      int m = e % MC + A.gen_xoff, o = e / MC;
       int a = o / n2, c = o % n2;
       double s1 = 0.0, s2 = 0.0;
       for (int b = 0; b < n1; ++b) {
@@ -822,7 +832,7 @@ __device__ __forceinline__ void digest_gen(const EriArgs& A, const double* blk, 
       if (s2 != 0.0) FX(o2 + c, o0 + a, -ck * s2);
     }
     for (int e = t; e < n0 * n3 * MC; e += ts) {  // (a,d)
-      int m = e % MC, o = e / MC;
+      int m = e % MC + A.gen_xoff, o = e / MC;
       int a = o / n3, d = o % n3;
       double s1 = 0.0, s2 = 0.0;
       for (int b = 0; b < n1; ++b) {
@@ -836,7 +846,7 @@ __device__ __forceinline__ void digest_gen(const EriArgs& A, const double* blk, 
       if (s2 != 0.0) FX(o3 + d, o0 + a, -ck * s2);
     }
     for (int e = t; e < n1 * n2 * MC; e += ts) {  // (b,c)
-      int m = e % MC, o = e / MC;
+      int m = e % MC + A.gen_xoff, o = e / MC;
       int b = o / n2, c = o % n2;
       double s1 = 0.0, s2 = 0.0;
       for (int a = 0; a < n0; ++a) {
@@ -850,7 +860,7 @@ __device__ __forceinline__ void digest_gen(const EriArgs& A, const double* blk, 
       if (s2 != 0.0) FX(o2 + c, o1 + b, -ck * s2);
     }
     for (int e = t; e < n1 * n3 * MC; e += ts) {  // (b,d)
-      int m = e % MC, o = e / MC;
+      int m = e % MC + A.gen_xoff, o = e / MC;
       int b = o / n3, d = o % n3;
       double s1 = 0.0, s2 = 0.0;
       for (int a = 0; a < n0; ++a) {
@@ -896,8 +906,8 @@ __device__ __forceinline__ void gen_contract(const EriArgs& A, const double* __r
   const double scale = COUL ? A.cj : -A.ck;
   if (mrows <= 0 || scale == 0.0) return;
   const size_t nbf = (size_t)A.nbf;
-  const double* __restrict__ P = A.Pgen;
-  double* __restrict__ F = A.Fgen;
+  const double* __restrict__ P = A.Pgen + (COUL ? 0 : A.gen_xoff);
+  double* __restrict__ F = A.Fgen + (COUL ? 0 : A.gen_xoff);
   if constexpr (USE_MMA) {
     const int kl = lane & 3, rl = lane >> 2;
     size_t pa1[KT], pa2[KT];
@@ -1045,7 +1055,7 @@ eri_kernel(const EriArgs A) {
   cart_xyz_rt(LB, ib, bx, by, bz);
   const int obx = (ax * (LB + 1) + bx) * NKL1, oby = (ay * (LB + 1) + by) * NKL1, obz = (az * (LB + 1) + bz) * NKL1;
 
-  const unsigned ntasks = *A.ntasks;
+  const unsigned ntasks = A.task_cap ? min(*A.ntasks, A.task_cap) : *A.ntasks;
   unsigned long long st_prim = 0, st_ints = 0;
 
   for (;;) {
@@ -1422,7 +1432,7 @@ struct RysSmem {
   static constexpr bool USE = R <= 3;
   __host__ __device__ static constexpr int doubles(int xmax) { return xmax * RysFmt<R>::DIV * STRIDE; }
 };
-// root r (as t^2) and its weight: two interleaved Clenshaw recurrences over 16-byte table loads
+// root r (as t^2) and its weight: two interleaved Horner recurrences over 16-byte table loads
 template <int R, bool SM>
 __device__ __forceinline__ void rys_pair(const EriArgs& a, const double* __restrict__ stab, const RysX& s, int r,
                                          double& t2, double& w) {
@@ -1444,19 +1454,161 @@ __device__ __forceinline__ void rys_pair(const EriArgs& a, const double* __restr
 #pragma unroll
     for (int k = 0; k < H; ++k) { p[k] = __ldg(ct + k); q[k] = __ldg(cw + k); }
   }
-  const double x2 = 2.0 * s.t;
-  double b1 = 0.0, b2 = 0.0, e1 = 0.0, e2 = 0.0;
+  // two interleaved Horner chains on the monomial coefficients (see rys_eval)
+  double b = p[H - 1].y, e = q[H - 1].y;
 #pragma unroll
-  for (int k = NCF - 1; k >= 1; --k) {
+  for (int k = NCF - 2; k >= 0; --k) {
     const double ck = (k & 1) ? p[k >> 1].y : p[k >> 1].x;
     const double dk = (k & 1) ? q[k >> 1].y : q[k >> 1].x;
-    const double b0 = fma(x2, b1, ck - b2);
-    const double e0 = fma(x2, e1, dk - e2);
-    b2 = b1; b1 = b0;
-    e2 = e1; e1 = e0;
+    b = fma(b, s.t, ck);
+    e = fma(e, s.t, dk);
   }
-  t2 = fma(s.t, b1, p[0].x - b2);
-  w = fma(s.t, e1, q[0].x - e2);
+  t2 = b;
+  w = e;
+}
+
+// Primitive-quartet loops of ONE shell quartet in one thread (WPQ: the slice of this lane): roots, 2-D VRR, HRR and the
+// assembly I += gx gy gz into acc[NCART4] (Cartesian, raw).  Shared by the task kernel and the run kernel below.
+template <int LA, int LB, int LC, int LD, bool GS, bool WPQ, int NTH>
+__device__ __forceinline__ void eval_quartet_thread(const EriArgs& A, const PairEntry& pb, const PairEntry& pk, double* gsm, int lane,
+                                                    double (&acc)[ClassCfg<LA, LB, LC, LD>::NCART4], bool& any,
+                                                    unsigned long long& st_prim) {
+  using Cfg = ClassCfg<LA, LB, LC, LD>;
+  constexpr int R = Cfg::R, NA = Cfg::NA, NB = Cfg::NB, NC = Cfg::NC, ND = Cfg::ND, NCART4 = Cfg::NCART4;
+  constexpr int NMAX = Cfg::NMAX, MMAX = Cfg::MMAX, NKL1 = Cfg::NKL1, NIJ1 = Cfg::NIJ1;
+  constexpr bool RSM = !GS && RysSmem<R>::USE;
+  (void)NA; (void)lane;
+  const double Ax = pb.ax, Ay = pb.ay, Az = pb.az, Cx = pk.ax, Cy = pk.ay, Cz = pk.az;
+  const double AB[3] = {pb.abx, pb.aby, pb.abz};
+  const double CD[3] = {pk.abx, pk.aby, pk.abz};
+#pragma unroll
+  for (int k = 0; k < NCART4; ++k) acc[k] = 0.0;
+  any = false;
+  // primitives are sorted by |K|/zeta: prune with (da db)^2 >= cut*(zeta+eta) >= cut*(zmin_bra+zmin_ket)
+  const double thr = A.prim_cutoff * (1.0 - 1e-9) * (pb.zmin + pk.zmin);
+  double da0 = 0.0;
+  if (pb.pcnt > 0) { const double* p0 = A.prim + (size_t)pb.poff * PRIM_STRIDE; da0 = __ldg(p0 + 4); }
+  // the primitive records of the NEXT iteration are loaded before the body of the current one (software pipeline:
+  // the L1 latency of these small dependent loads was 30 % of the stall samples of the contracted launches)
+  const double2* pq0 = reinterpret_cast<const double2*>(A.prim + (size_t)pk.poff * PRIM_STRIDE);
+  const double2* pp0 = reinterpret_cast<const double2*>(A.prim + (size_t)pb.poff * PRIM_STRIDE);
+  constexpr bool PIPE = prim_pipe<LA, LB, LC, LD>() && !WPQ;
+  // WPQ: lane = (lq, lp); ket primitives kq = lq, lq + QS, ...; bra primitives kp = lp, lp + 32/QS, ...
+  int kq0 = 0, kqs = 1, kp0 = 0, kps = 1;
+  if constexpr (WPQ) {
+    int qs = 1;
+    while (qs < 32 && qs < pk.pcnt) qs <<= 1;  // warp-uniform: all lanes hold the same quartet
+    kq0 = lane % qs; kqs = qs; kp0 = lane / qs; kps = 32 / qs;
+  }
+  double2 nq01 = make_double2(0, 0), nq23 = nq01, nq45 = nq01;
+  if (PIPE && pk.pcnt > 0) { nq01 = __ldg(pq0); nq23 = __ldg(pq0 + 1); nq45 = __ldg(pq0 + 2); }
+  for (int kq = kq0; kq < pk.pcnt; kq += kqs) {
+    if constexpr (!PIPE) { const double2* pq = pq0 + 3 * kq; nq01 = __ldg(pq); nq23 = __ldg(pq + 1); nq45 = __ldg(pq + 2); }
+    const double2 q01 = nq01, q23 = nq23, q45 = nq45;
+    if (PIPE && kq + 1 < pk.pcnt) {
+      const double2* pq = pq0 + 3 * (kq + 1);
+      nq01 = __ldg(pq); nq23 = __ldg(pq + 1); nq45 = __ldg(pq + 2);
+    }
+    const double Qx = q01.x, Qy = q01.y, Qz = q23.x, eta = q23.y, db = q45.x, einv = q45.y;
+    if ((da0 * db) * (da0 * db) < thr) break;
+    double2 np01 = make_double2(0, 0), np23 = np01, np45 = np01;
+    if (PIPE && pb.pcnt > 0) { np01 = __ldg(pp0); np23 = __ldg(pp0 + 1); np45 = __ldg(pp0 + 2); }
+    for (int kp = kp0; kp < pb.pcnt; kp += kps) {
+      double2 p01 = np01, p23 = np23, p45 = np45;
+      if constexpr (PIPE) {
+        if (kp + 1 < pb.pcnt) {
+          const double2* pp = pp0 + 3 * (kp + 1);
+          np01 = __ldg(pp); np23 = __ldg(pp + 1); np45 = __ldg(pp + 2);
+        }
+      } else {
+        const double2* pp = pp0 + 3 * kp;
+        p23 = __ldg(pp + 1); p45 = __ldg(pp + 2);
+      }
+      const double zeta = p23.y, zinv = p45.y;
+      const double pfac = p45.x * db;
+      if (pfac * pfac < thr) break;
+      const double ab = zeta + eta + zeta * eta * A.mu2inv;  // 2nd term: attenuated integrals, int_rys.F90:225-227
+      if (pfac * pfac < A.prim_cutoff * ab) continue;  // int_rys.F90:229-232
+      if constexpr (!PIPE) p01 = __ldg(pp0 + 3 * kp);
+      const double Px = p01.x, Py = p01.y, Pz = p23.x;
+      any = true;
+      ++st_prim;
+      const double rsab = rsqrt_nr(ab);
+      const double abinv = rsab * rsab;
+      const double rho = zeta * eta * abinv;
+      const double PQ[3] = {Px - Qx, Py - Qy, Pz - Qz};
+      const double PA[3] = {Px - Ax, Py - Ay, Pz - Az};
+      const double QC[3] = {Qx - Cx, Qy - Cy, Qz - Cz};
+      const double X = rho * (PQ[0] * PQ[0] + PQ[1] * PQ[1] + PQ[2] * PQ[2]);
+      const double pref = pfac * rsab;
+      const double rz = rho * zinv, re = rho * einv, hz = 0.5 * zinv, he = 0.5 * einv;
+      const RysX rx = rys_prepare<R>(A, X);
+#pragma unroll 1
+      for (int r = 0; r < R; ++r) {
+        double t2, w;
+        rys_pair<R, RSM>(A, gsm, rx, r, t2, w);
+        const double b10 = hz * (1.0 - t2 * rz), b01 = he * (1.0 - t2 * re), b00 = 0.5 * t2 * abinv;
+        constexpr int G3 = NIJ1 * NKL1;
+        double g[GS ? 1 : 3][GS ? 1 : G3];
+        double* gcol = gsm + threadIdx.x;
+        auto GSET = [&](int dir, int idx, double val) {
+          if constexpr (GS) gcol[(dir * G3 + idx) * NTH] = val;
+          else g[dir][idx] = val;
+        };
+#pragma unroll
+        for (int dir = 0; dir < 3; ++dir) {
+          const double c00 = PA[dir] - t2 * rz * PQ[dir];
+          const double d00 = QC[dir] + t2 * re * PQ[dir];
+          double v[NMAX][MMAX];
+          v[0][0] = dir == 0 ? w * pref : 1.0;
+#pragma unroll
+          for (int n = 1; n < NMAX; ++n) v[n][0] = c00 * v[n - 1][0] + (n >= 2 ? (n - 1) * b10 * v[n >= 2 ? n - 2 : 0][0] : 0.0);
+#pragma unroll
+          for (int m = 1; m < MMAX; ++m) {
+            v[0][m] = d00 * v[0][m - 1] + (m >= 2 ? (m - 1) * b01 * v[0][m >= 2 ? m - 2 : 0] : 0.0);
+#pragma unroll
+            for (int n = 1; n < NMAX; ++n)
+              v[n][m] = d00 * v[n][m - 1] + n * b00 * v[n - 1][m - 1] + (m >= 2 ? (m - 1) * b01 * v[n][m >= 2 ? m - 2 : 0] : 0.0);
+          }
+          // ket HRR then bra HRR
+          double h[NMAX][NKL1];
+#pragma unroll
+          for (int n = 0; n < NMAX; ++n) {
+#pragma unroll
+            for (int c = 0; c <= LC; ++c) h[n][c * (LD + 1)] = v[n][c];
+#pragma unroll
+            for (int d = 1; d <= LD; ++d) {
+#pragma unroll
+              for (int c = 0; c < MMAX - d; ++c) v[n][c] = v[n][c + 1] + CD[dir] * v[n][c];
+#pragma unroll
+              for (int c = 0; c <= LC; ++c) h[n][c * (LD + 1) + d] = v[n][c];
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < NKL1; ++k) {
+#pragma unroll
+            for (int a = 0; a <= LA; ++a) GSET(dir, (a * (LB + 1)) * NKL1 + k, h[a][k]);
+#pragma unroll
+            for (int b = 1; b <= LB; ++b) {
+#pragma unroll
+              for (int n = 0; n < NMAX - b; ++n) h[n][k] = h[n + 1][k] + AB[dir] * h[n][k];
+#pragma unroll
+              for (int a = 0; a <= LA; ++a) GSET(dir, (a * (LB + 1) + b) * NKL1 + k, h[a][k]);
+            }
+          }
+        }
+        static_for<0, NCART4>([&](auto I) {
+          constexpr int e = decltype(I)::value;
+          constexpr int id = e % ND, ic = (e / ND) % NC, ib = (e / (ND * NC)) % NB, ia = e / (ND * NC * NB);
+          constexpr int ix = (Cart<LA>::x(ia) * (LB + 1) + Cart<LB>::x(ib)) * NKL1 + Cart<LC>::x(ic) * (LD + 1) + Cart<LD>::x(id);
+          constexpr int iy = (Cart<LA>::y(ia) * (LB + 1) + Cart<LB>::y(ib)) * NKL1 + Cart<LC>::y(ic) * (LD + 1) + Cart<LD>::y(id);
+          constexpr int iz = (Cart<LA>::z(ia) * (LB + 1) + Cart<LB>::z(ib)) * NKL1 + Cart<LC>::z(ic) * (LD + 1) + Cart<LD>::z(id);
+          if constexpr (GS) acc[e] = fma(gcol[ix * NTH] * gcol[(G3 + iy) * NTH], gcol[(2 * G3 + iz) * NTH], acc[e]);
+          else acc[e] = fma(g[0][ix] * g[1][iy], g[2][iz], acc[e]);
+        });
+      }
+    }
+  }
 }
 
 // WPQ (warp per quartet): all 32 lanes work on ONE quartet and split its primitive quartets (ket primitives over
@@ -1473,7 +1625,7 @@ eri_small_kernel(const EriArgs A) {
   constexpr int NMAX = Cfg::NMAX, MMAX = Cfg::MMAX, NKL1 = Cfg::NKL1, NIJ1 = Cfg::NIJ1;
   constexpr int N0 = Shell<LA, PV>::NOUT, N1 = Shell<LB, PV>::NOUT, N2 = Shell<LC, PV>::NOUT, N3 = Shell<LD, PV>::NOUT;
   constexpr int NTOT = N0 * N1 * N2 * N3;
-  const unsigned ntasks = *A.ntasks;
+  const unsigned ntasks = A.task_cap ? min(*A.ntasks, A.task_cap) : *A.ntasks;
   unsigned long long st_prim = 0, st_ints = 0;
   constexpr bool RSM = !GS && RysSmem<R>::USE;  // Rys table of this nroots staged in shared memory
   if constexpr (RSM) {
@@ -1504,138 +1656,9 @@ eri_small_kernel(const EriArgs A) {
     if constexpr (DEN_EARLY) {
       if (A.mode == MODE_SYM) den_load<N0, N1, N2, N3>(A, 0, pb.oa, pb.ob, pk.oa, pk.ob, den0);
     }
-    const double Ax = pb.ax, Ay = pb.ay, Az = pb.az, Cx = pk.ax, Cy = pk.ay, Cz = pk.az;
-    const double AB[3] = {pb.abx, pb.aby, pb.abz};
-    const double CD[3] = {pk.abx, pk.aby, pk.abz};
     double acc[NCART4];
-#pragma unroll
-    for (int k = 0; k < NCART4; ++k) acc[k] = 0.0;
     bool any = false;
-    // primitives are sorted by |K|/zeta: prune with (da db)^2 >= cut*(zeta+eta) >= cut*(zmin_bra+zmin_ket)
-    const double thr = A.prim_cutoff * (1.0 - 1e-9) * (pb.zmin + pk.zmin);
-    double da0 = 0.0;
-    if (pb.pcnt > 0) { const double* p0 = A.prim + (size_t)pb.poff * PRIM_STRIDE; da0 = __ldg(p0 + 4); }
-    // the primitive records of the NEXT iteration are loaded before the body of the current one (software pipeline:
-    // the L1 latency of these small dependent loads was 30 % of the stall samples of the contracted launches)
-    const double2* pq0 = reinterpret_cast<const double2*>(A.prim + (size_t)pk.poff * PRIM_STRIDE);
-    const double2* pp0 = reinterpret_cast<const double2*>(A.prim + (size_t)pb.poff * PRIM_STRIDE);
-    constexpr bool PIPE = prim_pipe<LA, LB, LC, LD>() && !WPQ;
-    // WPQ: lane = (lq, lp); ket primitives kq = lq, lq + QS, ...; bra primitives kp = lp, lp + 32/QS, ...
-    int kq0 = 0, kqs = 1, kp0 = 0, kps = 1;
-    if constexpr (WPQ) {
-      int qs = 1;
-      while (qs < 32 && qs < pk.pcnt) qs <<= 1;  // warp-uniform: all lanes hold the same quartet
-      kq0 = lane % qs; kqs = qs; kp0 = lane / qs; kps = 32 / qs;
-    }
-    double2 nq01 = make_double2(0, 0), nq23 = nq01, nq45 = nq01;
-    if (PIPE && pk.pcnt > 0) { nq01 = __ldg(pq0); nq23 = __ldg(pq0 + 1); nq45 = __ldg(pq0 + 2); }
-    for (int kq = kq0; kq < pk.pcnt; kq += kqs) {
-      if constexpr (!PIPE) { const double2* pq = pq0 + 3 * kq; nq01 = __ldg(pq); nq23 = __ldg(pq + 1); nq45 = __ldg(pq + 2); }
-      const double2 q01 = nq01, q23 = nq23, q45 = nq45;
-      if (PIPE && kq + 1 < pk.pcnt) {
-        const double2* pq = pq0 + 3 * (kq + 1);
-        nq01 = __ldg(pq); nq23 = __ldg(pq + 1); nq45 = __ldg(pq + 2);
-      }
-      const double Qx = q01.x, Qy = q01.y, Qz = q23.x, eta = q23.y, db = q45.x, einv = q45.y;
-      if ((da0 * db) * (da0 * db) < thr) break;
-      double2 np01 = make_double2(0, 0), np23 = np01, np45 = np01;
-      if (PIPE && pb.pcnt > 0) { np01 = __ldg(pp0); np23 = __ldg(pp0 + 1); np45 = __ldg(pp0 + 2); }
-      for (int kp = kp0; kp < pb.pcnt; kp += kps) {
-        double2 p01 = np01, p23 = np23, p45 = np45;
-        if constexpr (PIPE) {
-          if (kp + 1 < pb.pcnt) {
-            const double2* pp = pp0 + 3 * (kp + 1);
-            np01 = __ldg(pp); np23 = __ldg(pp + 1); np45 = __ldg(pp + 2);
-          }
-        } else {
-          const double2* pp = pp0 + 3 * kp;
-          p23 = __ldg(pp + 1); p45 = __ldg(pp + 2);
-        }
-        const double zeta = p23.y, zinv = p45.y;
-        const double pfac = p45.x * db;
-        if (pfac * pfac < thr) break;
-        const double ab = zeta + eta + zeta * eta * A.mu2inv;  // 2nd term: attenuated integrals, int_rys.F90:225-227
-        if (pfac * pfac < A.prim_cutoff * ab) continue;  // int_rys.F90:229-232
-        if constexpr (!PIPE) p01 = __ldg(pp0 + 3 * kp);
-        const double Px = p01.x, Py = p01.y, Pz = p23.x;
-        any = true;
-        ++st_prim;
-        const double rsab = rsqrt_nr(ab);
-        const double abinv = rsab * rsab;
-        const double rho = zeta * eta * abinv;
-        const double PQ[3] = {Px - Qx, Py - Qy, Pz - Qz};
-        const double PA[3] = {Px - Ax, Py - Ay, Pz - Az};
-        const double QC[3] = {Qx - Cx, Qy - Cy, Qz - Cz};
-        const double X = rho * (PQ[0] * PQ[0] + PQ[1] * PQ[1] + PQ[2] * PQ[2]);
-        const double pref = pfac * rsab;
-        const double rz = rho * zinv, re = rho * einv, hz = 0.5 * zinv, he = 0.5 * einv;
-        const RysX rx = rys_prepare<R>(A, X);
-#pragma unroll 1
-        for (int r = 0; r < R; ++r) {
-          double t2, w;
-          rys_pair<R, RSM>(A, gsm, rx, r, t2, w);
-          const double b10 = hz * (1.0 - t2 * rz), b01 = he * (1.0 - t2 * re), b00 = 0.5 * t2 * abinv;
-          constexpr int G3 = NIJ1 * NKL1;
-          double g[GS ? 1 : 3][GS ? 1 : G3];
-          double* gcol = gsm + threadIdx.x;
-          auto GSET = [&](int dir, int idx, double val) {
-            if constexpr (GS) gcol[(dir * G3 + idx) * NTH] = val;
-            else g[dir][idx] = val;
-          };
-#pragma unroll
-          for (int dir = 0; dir < 3; ++dir) {
-            const double c00 = PA[dir] - t2 * rz * PQ[dir];
-            const double d00 = QC[dir] + t2 * re * PQ[dir];
-            double v[NMAX][MMAX];
-            v[0][0] = dir == 0 ? w * pref : 1.0;
-#pragma unroll
-            for (int n = 1; n < NMAX; ++n) v[n][0] = c00 * v[n - 1][0] + (n >= 2 ? (n - 1) * b10 * v[n >= 2 ? n - 2 : 0][0] : 0.0);
-#pragma unroll
-            for (int m = 1; m < MMAX; ++m) {
-              v[0][m] = d00 * v[0][m - 1] + (m >= 2 ? (m - 1) * b01 * v[0][m >= 2 ? m - 2 : 0] : 0.0);
-#pragma unroll
-              for (int n = 1; n < NMAX; ++n)
-                v[n][m] = d00 * v[n][m - 1] + n * b00 * v[n - 1][m - 1] + (m >= 2 ? (m - 1) * b01 * v[n][m >= 2 ? m - 2 : 0] : 0.0);
-            }
-            // ket HRR then bra HRR
-            double h[NMAX][NKL1];
-#pragma unroll
-            for (int n = 0; n < NMAX; ++n) {
-#pragma unroll
-              for (int c = 0; c <= LC; ++c) h[n][c * (LD + 1)] = v[n][c];
-#pragma unroll
-              for (int d = 1; d <= LD; ++d) {
-#pragma unroll
-                for (int c = 0; c < MMAX - d; ++c) v[n][c] = v[n][c + 1] + CD[dir] * v[n][c];
-#pragma unroll
-                for (int c = 0; c <= LC; ++c) h[n][c * (LD + 1) + d] = v[n][c];
-              }
-            }
-#pragma unroll
-            for (int k = 0; k < NKL1; ++k) {
-#pragma unroll
-              for (int a = 0; a <= LA; ++a) GSET(dir, (a * (LB + 1)) * NKL1 + k, h[a][k]);
-#pragma unroll
-              for (int b = 1; b <= LB; ++b) {
-#pragma unroll
-                for (int n = 0; n < NMAX - b; ++n) h[n][k] = h[n + 1][k] + AB[dir] * h[n][k];
-#pragma unroll
-                for (int a = 0; a <= LA; ++a) GSET(dir, (a * (LB + 1) + b) * NKL1 + k, h[a][k]);
-              }
-            }
-          }
-          static_for<0, NCART4>([&](auto I) {
-            constexpr int e = decltype(I)::value;
-            constexpr int id = e % ND, ic = (e / ND) % NC, ib = (e / (ND * NC)) % NB, ia = e / (ND * NC * NB);
-            constexpr int ix = (Cart<LA>::x(ia) * (LB + 1) + Cart<LB>::x(ib)) * NKL1 + Cart<LC>::x(ic) * (LD + 1) + Cart<LD>::x(id);
-            constexpr int iy = (Cart<LA>::y(ia) * (LB + 1) + Cart<LB>::y(ib)) * NKL1 + Cart<LC>::y(ic) * (LD + 1) + Cart<LD>::y(id);
-            constexpr int iz = (Cart<LA>::z(ia) * (LB + 1) + Cart<LB>::z(ib)) * NKL1 + Cart<LC>::z(ic) * (LD + 1) + Cart<LD>::z(id);
-            if constexpr (GS) acc[e] = fma(gcol[ix * NTH] * gcol[(G3 + iy) * NTH], gcol[(2 * G3 + iz) * NTH], acc[e]);
-            else acc[e] = fma(g[0][ix] * g[1][iy], g[2][iz], acc[e]);
-          });
-        }
-      }
-    }
+    eval_quartet_thread<LA, LB, LC, LD, GS, WPQ, NTH>(A, pb, pk, gsm, lane, acc, any, st_prim);
     if constexpr (WPQ) {
       any = __any_sync(0xffffffffu, any);
 #pragma unroll
@@ -1735,6 +1758,229 @@ eri_small_kernel(const EriArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Run kernel (MODE_SYM, one Fock matrix): the thread-per-quartet evaluation above, but a WARP walks a run of up to
+// RUN_LEN consecutive surviving kets of ONE bra (k_enum writes a bra's survivors contiguously and cuts them into warp
+// items); lane l takes the kets l, l + 32, ... of the run, so the lanes of one step still hold neighbouring kets
+// (coalesced pair entries / primitive records, shared density rows).  The bra entry and D_ab are loaded once per run,
+// J_ab is accumulated in registers over the whole run (one butterfly + one red per element and run instead of a
+// segmented shuffle reduction per step); K_ac / K_bc keep the per-step segmented reduction over the lanes that share the
+// ket shell c.  A lane-private run (lane l = kets l*M .. l*M+M-1, K_ac / K_bc in registers too) removed 28-42 % of the
+// instructions of the uncontracted launches but was 15 % SLOWER overall: lanes 16 kets apart share no cache lines.
+constexpr int RUN_LEN = 32 * OQPB_RUN_M;  // <= 255 (the length shares a word with the bra index): OQPB_RUN_M <= 7
+static_assert(RUN_LEN <= 255, "OQPB_RUN_M");
+template <int N0, int N1, int N2, int N3, bool SEGC>
+__device__ __forceinline__ void digest_run(const EriArgs& A, const double (&v)[N0 * N1 * N2 * N3], const double (&dab)[N0 * N1],
+                                           int o0, int o1, int o2, int o3, double (&jab)[N0 * N1], const SegMask& mc) {
+  const unsigned nbf = (unsigned)A.nbf;
+  const double c4 = 4.0 * A.cj, c1 = A.ck;
+  const double* __restrict__ DJ = A.DJ[0];
+  const double* __restrict__ DK = A.DK[0];
+  double* __restrict__ F = A.F[0];
+#define VV(a, b, c, d) v[(((a)*N1 + (b)) * N2 + (c)) * N3 + (d)]
+  {  // J_ab += sum_cd v D_cd   (4 cj at the flush)
+    double dd[N2 * N3];
+#pragma unroll
+    for (int c = 0; c < N2; ++c)
+#pragma unroll
+      for (int d = 0; d < N3; ++d) dd[c * N3 + d] = __ldg(DJ + ((unsigned)(o2 + c) * nbf + (unsigned)(o3 + d)));
+#pragma unroll
+    for (int a = 0; a < N0; ++a)
+#pragma unroll
+      for (int b = 0; b < N1; ++b) {
+        double sum = jab[a * N1 + b];
+#pragma unroll
+        for (int c = 0; c < N2; ++c)
+#pragma unroll
+          for (int d = 0; d < N3; ++d) sum = fma(VV(a, b, c, d), dd[c * N3 + d], sum);
+        jab[a * N1 + b] = sum;
+      }
+  }
+  {  // J_cd += 4 cj sum_ab v D_ab
+#pragma unroll
+    for (int c = 0; c < N2; ++c)
+#pragma unroll
+      for (int d = 0; d < N3; ++d) {
+        double sum = 0.0;
+#pragma unroll
+        for (int a = 0; a < N0; ++a)
+#pragma unroll
+          for (int b = 0; b < N1; ++b) sum = fma(VV(a, b, c, d), dab[a * N1 + b], sum);
+        if (sum != 0.0) atomicAdd(F + tri_u(o2 + c, o3 + d), c4 * sum);
+      }
+  }
+  {  // K_ac -= ck sum_bd v D_bd
+    double dd[N1 * N3];
+#pragma unroll
+    for (int b = 0; b < N1; ++b)
+#pragma unroll
+      for (int d = 0; d < N3; ++d) dd[b * N3 + d] = __ldg(DK + ((unsigned)(o1 + b) * nbf + (unsigned)(o3 + d)));
+#pragma unroll
+    for (int a = 0; a < N0; ++a)
+#pragma unroll
+      for (int c = 0; c < N2; ++c) {
+        double sum = 0.0;
+#pragma unroll
+        for (int b = 0; b < N1; ++b)
+#pragma unroll
+          for (int d = 0; d < N3; ++d) sum = fma(VV(a, b, c, d), dd[b * N3 + d], sum);
+        if constexpr (SEGC) sum = seg_sum(sum, mc);
+        if ((!SEGC || mc.head) && sum != 0.0) atomicAdd(F + tri_u(o0 + a, o2 + c), -c1 * sum);
+      }
+  }
+  {  // K_ad -= ck sum_bc v D_bc
+    double dd[N1 * N2];
+#pragma unroll
+    for (int b = 0; b < N1; ++b)
+#pragma unroll
+      for (int c = 0; c < N2; ++c) dd[b * N2 + c] = __ldg(DK + ((unsigned)(o1 + b) * nbf + (unsigned)(o2 + c)));
+#pragma unroll
+    for (int a = 0; a < N0; ++a)
+#pragma unroll
+      for (int d = 0; d < N3; ++d) {
+        double sum = 0.0;
+#pragma unroll
+        for (int b = 0; b < N1; ++b)
+#pragma unroll
+          for (int c = 0; c < N2; ++c) sum = fma(VV(a, b, c, d), dd[b * N2 + c], sum);
+        if (sum != 0.0) atomicAdd(F + tri_u(o0 + a, o3 + d), -c1 * sum);
+      }
+  }
+  {  // K_bc -= ck sum_ad v D_ad
+    double dd[N0 * N3];
+#pragma unroll
+    for (int a = 0; a < N0; ++a)
+#pragma unroll
+      for (int d = 0; d < N3; ++d) dd[a * N3 + d] = __ldg(DK + ((unsigned)(o0 + a) * nbf + (unsigned)(o3 + d)));
+#pragma unroll
+    for (int b = 0; b < N1; ++b)
+#pragma unroll
+      for (int c = 0; c < N2; ++c) {
+        double sum = 0.0;
+#pragma unroll
+        for (int a = 0; a < N0; ++a)
+#pragma unroll
+          for (int d = 0; d < N3; ++d) sum = fma(VV(a, b, c, d), dd[a * N3 + d], sum);
+        if constexpr (SEGC) sum = seg_sum(sum, mc);
+        if ((!SEGC || mc.head) && sum != 0.0) atomicAdd(F + tri_u(o1 + b, o2 + c), -c1 * sum);
+      }
+  }
+  {  // K_bd -= ck sum_ac v D_ac
+    double dd[N0 * N2];
+#pragma unroll
+    for (int a = 0; a < N0; ++a)
+#pragma unroll
+      for (int c = 0; c < N2; ++c) dd[a * N2 + c] = __ldg(DK + ((unsigned)(o0 + a) * nbf + (unsigned)(o2 + c)));
+#pragma unroll
+    for (int b = 0; b < N1; ++b)
+#pragma unroll
+      for (int d = 0; d < N3; ++d) {
+        double sum = 0.0;
+#pragma unroll
+        for (int a = 0; a < N0; ++a)
+#pragma unroll
+          for (int c = 0; c < N2; ++c) sum = fma(VV(a, b, c, d), dd[a * N2 + c], sum);
+        if (sum != 0.0) atomicAdd(F + tri_u(o1 + b, o3 + d), -c1 * sum);
+      }
+  }
+#undef VV
+}
+
+// the run kernel carries 2 N0 N1 more doubles than the task kernel: keep the classes that sat just under 128 registers there
+template <int LA, int LB, int LC, int LD>
+__host__ __device__ constexpr int run_regcap() {
+  constexpr int key = LA * 1000 + LB * 100 + LC * 10 + LD;
+  return (key == 1000 || key == 0) ? 128 : small_regcap<LA, LB, LC, LD>();
+}
+template <int LA, int LB, int LC, int LD, int PV, bool GS>
+__global__ void __launch_bounds__(GS ? MEDIUM_NT : SMALL_NT, GS ? min_ctas(MEDIUM_NT, OQPB_MED_REGS) : min_ctas(SMALL_NT, run_regcap<LA, LB, LC, LD>()))
+eri_run_kernel(const EriArgs A) {
+  constexpr int NTH = GS ? MEDIUM_NT : SMALL_NT;
+  constexpr int WPC = NTH / 32;
+  extern __shared__ double gsm[];
+  using Cfg = ClassCfg<LA, LB, LC, LD>;
+  constexpr int R = Cfg::R, NA = Cfg::NA, NB = Cfg::NB, NC = Cfg::NC, NCART4 = Cfg::NCART4;
+  constexpr int N0 = Shell<LA, PV>::NOUT, N1 = Shell<LB, PV>::NOUT, N2 = Shell<LC, PV>::NOUT, N3 = Shell<LD, PV>::NOUT;
+  constexpr int NTOT = N0 * N1 * N2 * N3;
+  constexpr bool RSM = !GS && RysSmem<R>::USE;
+  constexpr unsigned FULL = 0xffffffffu;
+  unsigned long long st_prim = 0, st_ints = 0;
+  if constexpr (RSM) {
+    const int nint = A.rys_xmax * RysFmt<R>::DIV;
+    for (int i = threadIdx.x; i < nint * RysSmem<R>::ROW; i += NTH)
+      gsm[(i / RysSmem<R>::ROW) * RysSmem<R>::STRIDE + i % RysSmem<R>::ROW] = A.rys_tab[i];
+    __syncthreads();
+  }
+  const unsigned nitems = min(*A.nitems, A.item_cap);
+  const int lane = threadIdx.x & 31;
+  double* __restrict__ F = A.F[0];
+  const double c4 = 4.0 * A.cj, cut = A.cutoff;
+  const unsigned nbf = (unsigned)A.nbf;
+  for (unsigned it = blockIdx.x * WPC + (threadIdx.x >> 5); it < nitems; it += gridDim.x * WPC) {
+    const int2 item = A.items[it];  // warp-uniform
+    const int len = (int)((unsigned)item.x >> 24);
+    if (len == 0) continue;
+    const PairEntry pb = A.bra[item.x & 0xffffff];
+    const unsigned start = (unsigned)item.y;
+    double jab[N0 * N1], dab[N0 * N1];
+#pragma unroll
+    for (int a = 0; a < N0; ++a)
+#pragma unroll
+      for (int b = 0; b < N1; ++b) {
+        jab[a * N1 + b] = 0.0;
+        dab[a * N1 + b] = __ldg(A.DJ[0] + ((unsigned)(pb.oa + a) * nbf + (unsigned)(pb.ob + b)));
+      }
+#pragma unroll 1
+    for (int i0 = 0; i0 < len; i0 += 32) {
+      const int idx = i0 + lane;
+      const bool act = idx < len;
+      PairEntry pk = A.ket[A.tasks[start + (act ? idx : 0)].y];
+      if (!act) pk.pcnt = 0;  // no primitive work, zero block
+      double acc[NCART4];
+      bool any = false;
+      eval_quartet_thread<LA, LB, LC, LD, GS, false, NTH>(A, pb, pk, gsm, lane, acc, any, st_prim);
+      if (!GS && !__any_sync(FULL, any)) continue;  // (the K reductions of the register classes are warp collectives)
+      if (GS && !any) continue;
+      // normalisation / pure projection in registers, index by index: d, c, b, a
+      double b3[NA * NB * NC * N3], b2[NA * NB * N2 * N3], b1[NA * N1 * N2 * N3], blk[NTOT];
+      proj_reg<LD, Shell<LD, PV>::PURE, NA * NB * NC, 1>(acc, b3);
+      proj_reg<LC, Shell<LC, PV>::PURE, NA * NB, N3>(b3, b2);
+      proj_reg<LB, Shell<LB, PV>::PURE, NA, N2 * N3>(b2, b1);
+      proj_reg<LA, Shell<LA, PV>::PURE, 1, N1 * N2 * N3>(b1, blk);
+      // element cutoff (int2.F90:1806-1812) and shell-level coincidence factor (int2.F90:1849-1851)
+      float facf = 1.0f;
+      if (pb.sa == pb.sb) facf *= 0.5f;
+      if (pk.sa == pk.sb) facf *= 0.5f;
+      if (pb.sa == pk.sa && pb.sb == pk.sb) facf *= 0.5f;
+      const double fac = (double)facf;
+      unsigned nz = 0;
+#pragma unroll
+      for (int e = 0; e < NTOT; ++e) {
+        const double v = blk[e];
+        const bool z = fabs(v) < cut;
+        nz += !z;
+        blk[e] = z ? 0.0 : v * fac;
+      }
+      st_ints += (unsigned long long)nz * (unsigned)(8.0f * facf);
+      SegMask mc;
+      if constexpr (!GS) mc = seg_make(act ? (long long)pk.sa : -1 - (long long)lane, lane);  // runs of equal ket shell c
+      digest_run<N0, N1, N2, N3, !GS>(A, blk, dab, pb.oa, pb.ob, pk.oa, pk.ob, jab, mc);
+    }
+    // J_ab of the whole run: butterfly over the lanes, lane (e mod 32) issues the red of element e
+#pragma unroll
+    for (int e = 0; e < N0 * N1; ++e) {
+      double v = jab[e];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+      if (lane == (e & 31) && v != 0.0) atomicAdd(F + tri_u(pb.oa + e / N1, pb.ob + e % N1), c4 * v);
+    }
+  }
+  if (A.stat) {
+    if (st_prim) atomicAdd(A.stat, st_prim);
+    if (st_ints) atomicAdd(A.stat + 1, st_ints);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Group kernel for the large classes: a quartet is owned by an aligned group of G lanes of ONE warp
 // (G = 4, 8, 16 or 32), a warp works on 32/G quartets at once, and every phase boundary is a __syncwarp():
 // no CTA barrier anywhere, warps fetch their own work.  Each lane owns NVL = ceil(NA*NB/G) bra Cartesian
@@ -1805,7 +2051,7 @@ eri_group_kernel(const EriArgs A) {
     cart_xyz_rt(LB, ib, bx, by, bz);
     obx[j] = ax * (LB + 1) + bx; oby[j] = ay * (LB + 1) + by; obz[j] = az * (LB + 1) + bz;  // table layout [c][d][a][b]
   }
-  const unsigned ntasks = *A.ntasks;
+  const unsigned ntasks = A.task_cap ? min(*A.ntasks, A.task_cap) : *A.ntasks;
   unsigned long long st_prim = 0, st_ints = 0;
 
   for (;;) {
@@ -2212,6 +2458,49 @@ cudaError_t launch_eri_wpq(const EriArgs& args, int nblocks, cudaStream_t st) {
     return cudaErrorNotSupported;
   }
 }
+// run-kernel launch (thread-per-quartet classes, MODE_SYM with one Fock matrix)
+template <int LA, int LB, int LC, int LD, int PV>
+cudaError_t launch_eri_run(const EriArgs& args, int nblocks, cudaStream_t st) {
+  using Cfg = ClassCfg<LA, LB, LC, LD>;
+  if constexpr (Cfg::NCART4 <= SMALL_MAX) {
+    constexpr int R = Cfg::R;
+    const size_t smem = RysSmem<R>::USE ? (size_t)RysSmem<R>::doubles(args.rys_xmax) * sizeof(double) : 0;
+    static DevFlags flags;
+    bool& attr_set = flags.cur();
+    if (!attr_set && smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(eri_run_kernel<LA, LB, LC, LD, PV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    eri_run_kernel<LA, LB, LC, LD, PV, false><<<nblocks, SMALL_NT, smem, st>>>(args);
+    return cudaGetLastError();
+  } else if constexpr (Cfg::NCART4 <= MEDIUM_MAX) {
+    constexpr size_t smem0 = (size_t)3 * Cfg::NIJ1 * Cfg::NKL1 * MEDIUM_NT * sizeof(double);
+    // OQPB_MED_CTAS=n: pad the dynamic shared memory so that at most n CTAs share an SM (fewer resident threads -> the
+    // register spills of the >= 90-Cartesian classes stay in L1; experiment knob)
+    static const int want = getenv("OQPB_MED_CTAS") ? atoi(getenv("OQPB_MED_CTAS")) : 0;
+    const size_t smem = want > 0 ? std::max(smem0, (size_t)(227 * 1024 / (want + 1) + 1024)) : smem0;
+    static DevFlags flags;
+    bool& attr_set = flags.cur();
+    if (!attr_set && smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(eri_run_kernel<LA, LB, LC, LD, PV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    eri_run_kernel<LA, LB, LC, LD, PV, true><<<nblocks, MEDIUM_NT, smem, st>>>(args);
+    return cudaGetLastError();
+  } else {
+    return cudaErrorNotSupported;
+  }
+}
+template <int LA, int LB, int LC, int LD>
+constexpr bool class_has_run() {
+#ifdef OQPB_RUN_SMALL_ONLY
+  return ClassCfg<LA, LB, LC, LD>::NCART4 <= SMALL_MAX;
+#else
+  return ClassCfg<LA, LB, LC, LD>::NCART4 <= MEDIUM_MAX;
+#endif
+}
 template <int LA, int LB, int LC, int LD>
 constexpr bool class_has_wpq() { return ClassCfg<LA, LB, LC, LD>::NCART4 <= SMALL_MAX; }
 
@@ -2230,7 +2519,7 @@ constexpr int class_max_ctas() {
 }
 
 using LaunchFn = cudaError_t (*)(const EriArgs&, int, cudaStream_t);
-struct ClassEntry { LaunchFn launch; int qpb; int nt; size_t smem; int maxcta; LaunchFn launch_wpq; };
+struct ClassEntry { LaunchFn launch; int qpb; int nt; size_t smem; int maxcta; LaunchFn launch_wpq; LaunchFn launch_run; };
 // class table: [pure variant PV = (d pure) | (f pure) << 1][quartet class]
 const ClassEntry* class_table(int pv);
 

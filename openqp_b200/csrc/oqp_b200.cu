@@ -11,7 +11,10 @@
 //   k_fock_post                  fock_jk post-scaling                             scf_addons.F90:1177-1185
 // There is no CPU fallback: every compute entry needs a CUDA device.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is dlopen()ed when a multi-device context is created
 #include <chrono>
+#include <thread>
 
 #include <algorithm>
 #include <cmath>
@@ -135,6 +138,7 @@ struct BuildPlan {
   std::vector<size_t> km_off;
   std::vector<std::pair<int, int>> cps;
   long long total_local = 0;
+  DevBuf d_km;  // this plan's own ket-bound arrays (a shared buffer let the attenuated pass overwrite the regular plan's)
 };
 
 struct oqpb_ctx {
@@ -161,11 +165,13 @@ struct oqpb_ctx {
   // work
   static constexpr int NSTREAM = 8;  // launch lanes (nlanes of them used): chunk c runs on lane c % NSTREAM (own task buffer) so that the
                                      // tail of one class kernel overlaps the next enumeration / class kernel
-  DevBuf d_tasks[NSTREAM], d_counters, d_Dsq, d_F, d_Din, d_stats, d_gen_in, d_gen_out;
+  DevBuf d_tasks[NSTREAM], d_items[NSTREAM], d_counters, d_Dsq, d_F, d_Din, d_stats, d_gen_in, d_gen_out;
   cudaStream_t lane[NSTREAM] = {};
   cudaEvent_t lane_ev[NSTREAM] = {};
   int nlanes = 4;      // OQPB_NLANES
   int grid_pct = 100;  // OQPB_GRID_PCT: scales the per-class grid caps
+  bool use_run = true;   // OQPB_RUN=0: task kernels only
+  int run_max_bucket_sum = 2;  // OQPB_RUN_BUCKETS
   size_t wpq_max_tasks = 16384;  // OQPB_WPQ_MAX: largest launch (candidate quartets) that uses the warp-per-quartet kernels
   cudaEvent_t fork_ev = nullptr;
   size_t task_cap = (size_t)1 << 23;
@@ -180,6 +186,13 @@ struct oqpb_ctx {
   unsigned* h_counts = nullptr;  // pinned
   size_t h_counts_cap = 0;
   double fp64_peak = 0;
+  // multi-device context (oqpb_ctx_create_multi): the master holds the peers; every member has its communicator
+  std::vector<oqpb_ctx*> peers;  // master only: devices 1 .. ndev-1
+  ncclComm_t comm = nullptr;
+  int mdev = 0, mndev = 1;       // index of this member / number of members
+  int base_rank = 0, base_nranks = 1;  // partition requested by the caller (MPI rank split), before the device split
+  DevBuf d_mask;  // optional bra shell-pair mask (oqpb_set_bra_mask)
+  bool have_mask = false;
   BuildPlan plan[2];  // [0] regular, [1] attenuated pass
   long plan_gen = 0;  // bumped by set_basis / set_cutoff / set_screening / set_partition
 };
@@ -320,13 +333,15 @@ __global__ void k_shlden_gen(int nshell, long npairs, const int* __restrict__ ao
 }
 
 // per-entry build data: ok = bra-level test passes (screen_ij, int2.F90:763-772); d4 = 4*dsh(sa,sb)
+// mask (optional): bra shell pairs (canonical id i(i+1)/2+j) taking part in this build -- the sampled-parity hook
 __global__ void k_entry_screen(long nent, const PairEntry* __restrict__ ent, const double* __restrict__ Q,
                                const double* __restrict__ dsh, int nshell, const unsigned long long* maxden,
-                               double cutoff, int* __restrict__ ok, double* __restrict__ d4) {
+                               double cutoff, int* __restrict__ ok, double* __restrict__ d4,
+                               const int* __restrict__ canon, const unsigned char* __restrict__ mask) {
   long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nent) return;
   double md = __longlong_as_double((long long)*maxden);
-  ok[e] = !(__dmul_rn(Q[e], md) < cutoff);
+  ok[e] = !(__dmul_rn(Q[e], md) < cutoff) && (mask == nullptr || mask[canon[e]] != 0);
   d4[e] = 4.0 * dsh[(size_t)ent[e].sa * nshell + ent[e].sb];
 }
 
@@ -343,10 +358,10 @@ k_enum(const PairEntry* __restrict__ bra, const PairEntry* __restrict__ ket, con
        const int* __restrict__ okb, const int* __restrict__ okk, const int* __restrict__ canb,
        const int* __restrict__ cank, const int* __restrict__ kmax, int p0, int p1, int pstride, int diag,
        const double* __restrict__ dsh, int nshell, double cutoff, int2* __restrict__ tasks, unsigned* __restrict__ count,
-       unsigned cap, int use_smem) {
+       unsigned cap, int use_smem, int2* __restrict__ items, unsigned* __restrict__ nitems, unsigned item_cap) {
   extern __shared__ double rows[];
   __shared__ unsigned s_w[ENUM_NT / 32];
-  __shared__ unsigned s_base;
+  __shared__ unsigned s_base, s_ibase;
   int p = p0 + blockIdx.x * pstride;
   if (p >= p1) return;
   const PairEntry eb = bra[p];
@@ -385,10 +400,20 @@ k_enum(const PairEntry* __restrict__ bra, const PairEntry* __restrict__ ket, con
     for (int k = 0; k < ENUM_NT / 32; ++k) tot += s_w[k];
     s_base = tot ? atomicAdd(count, tot) : 0u;
     s_w[0] = tot;  // reused as flag below
+    // warp work items of the run kernels: the bra's contiguous survivors cut into pieces of RUN_LEN kets
+    if (items && tot) s_ibase = atomicAdd(nitems, (tot + RUN_LEN - 1) / RUN_LEN);
   }
   __syncthreads();
   if (s_w[0] == 0) return;
   unsigned running = s_base;
+  if (items) {
+    const unsigned tot = s_w[0], nit = (tot + RUN_LEN - 1) / RUN_LEN;
+    for (unsigned k = threadIdx.x; k < nit; k += ENUM_NT) {
+      const unsigned start = running + k * RUN_LEN, len = min((unsigned)RUN_LEN, tot - k * RUN_LEN);
+      if (s_ibase + k < item_cap)  // a piece past the task buffer gets length 0 (the host reports the overflow)
+        items[s_ibase + k] = make_int2((int)((unsigned)p | ((start + len <= cap ? len : 0u) << 24)), (int)start);
+    }
+  }
   __syncthreads();
   // pass 2: write in ket-list order
   for (int q0 = 0; q0 < nk; q0 += ENUM_NT) {
@@ -451,6 +476,35 @@ __global__ void k_td_unpack(const double* __restrict__ X, double* __restrict__ o
   int v = (int)(e / n2);
   long r = e % n2;
   out[e] = X[(size_t)r * NM + comp * nvec + v];
+}
+
+// Generic J/K: slab m of the interleaved X[(nu*nbf+mu)*NM + m] from a column-major nbf x nbf matrix P (mu fastest):
+// op 0: P   1: P + P^T   2: P^T - P   3: P^T ; accumulate != 0 adds to the slab (sums of matrices)
+__global__ void k_slab_pack(const double* __restrict__ P, double* __restrict__ X, int nbf, int NM, int m, int op, int accumulate) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long)nbf * nbf) return;
+  int nu = (int)(e / nbf), mu = (int)(e % nbf);
+  double p = P[e], pt = P[(size_t)mu * nbf + nu];
+  double v = op == 0 ? p : (op == 1 ? p + pt : (op == 2 ? pt - p : pt));
+  double* x = X + (size_t)e * NM + m;
+  *x = accumulate ? *x + v : v;
+}
+__global__ void k_slab_unpack(const double* __restrict__ X, double* __restrict__ out, int nbf, int NM, int m, double scale, int accumulate) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long)nbf * nbf) return;
+  double v = scale * X[(size_t)e * NM + m];
+  out[e] = accumulate ? out[e] + v : v;
+}
+// UMRSF: components 9 and 10 (0-based 8, 9) of d3(v, c, mu, nu) enter the exchange transposed (tdhf_mrsf_lib.F90:393-400)
+__global__ void k_umrsf_prepare(const double* __restrict__ d3, double* __restrict__ X, int nbf, int nvec, int ncomp) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int NM = nvec * ncomp;
+  if (e >= (long)nbf * nbf * NM) return;
+  int m = (int)(e % NM);
+  long r = e / NM;
+  int nu = (int)(r / nbf), mu = (int)(r % nbf);
+  int c = m / nvec;
+  X[e] = (c == 8 || c == 9) ? d3[((size_t)mu * nbf + nu) * NM + m] : d3[e];
 }
 
 __global__ void k_rys_test(EriArgs A, int nroots, int npts, const double* x, double* t2, double* w) {
@@ -614,6 +668,22 @@ int build_pairtable(oqpb_ctx* ctx, const Cutoffs& c, PairTable& T, const std::ve
   return OQPB_OK;
 }
 
+// c0 + sum_k c_k T_k(t)  ->  sum_j a_j t^j for every block of nc coefficients, accumulated in long double (the integer
+// Chebyshev coefficients grow to 2^(nc-2): 64-bit mantissas keep the result correctly rounded to double)
+void cheb_to_monomial(const double* in, size_t n, int nc, double* out) {
+  std::vector<std::vector<long double>> T(nc, std::vector<long double>(nc, 0.0L));  // T[k][j]: coefficient of t^j in T_k
+  T[0][0] = 1.0L;
+  if (nc > 1) T[1][1] = 1.0L;
+  for (int k = 2; k < nc; ++k)
+    for (int j = 0; j < nc; ++j) T[k][j] = (j > 0 ? 2.0L * T[k - 1][j - 1] : 0.0L) - T[k - 2][j];
+  for (size_t b = 0; b + nc <= n; b += nc)
+    for (int j = 0; j < nc; ++j) {
+      long double a = 0.0L;
+      for (int k = nc - 1; k >= j; --k) a += (long double)in[b + k] * T[k][j];
+      out[b + j] = (double)a;
+    }
+}
+
 // table of one nroots: the fine format (RysFmt<R>, quarter intervals x 8 terms) for nroots <= RYSF_MAXR
 static_assert(RYS_FINE_MAXR <= RYSF_MAXR && RYSF_NCOEF == RysFmt<1>::NC && RYSF_DIV == RysFmt<1>::DIV &&
                   RYS_NCOEF == RysFmt<3>::NC,
@@ -716,6 +786,7 @@ struct BuildSpec {
   double* Fgen = nullptr;
   int gen_nm = 0, gen_ncoul = 0, gen_nvec = 0;
   int gen_mcount = -1;  // matrices taking the exchange part (default: all gen_nm)
+  int gen_xoff = 0;     // ... starting at this matrix
   double cj = 0, ck = 0;
   double digest_flops_per_int = 0;
   bool attenuated = false;  // CAM second pass: attenuated integrals + attenuated Schwarz bounds (ctx->run.att_mu)
@@ -738,7 +809,8 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   CK(ctx->d_d4.ensure(nent * sizeof(double)));
   k_entry_screen<<<(unsigned)((nent + 255) / 256), 256, 0, ctx->stream>>>(
       nent, T.d_ent.as<PairEntry>(), dQ, ctx->d_dsh.as<double>(), ns,
-      ctx->d_maxden.as<unsigned long long>(), cutoff, ctx->d_ok.as<int>(), ctx->d_d4.as<double>());
+      ctx->d_maxden.as<unsigned long long>(), cutoff, ctx->d_ok.as<int>(), ctx->d_d4.as<double>(),
+      T.d_canon.as<int>(), ctx->have_mask ? ctx->d_mask.as<unsigned char>() : nullptr);
   CK(cudaGetLastError());
   static const bool timing = getenv("OQPB_TIMING") != nullptr;
   auto tnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -756,7 +828,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   double bound4p = bound4;
   if (bound4 > 0) { int e; std::frexp(bound4, &e); bound4p = std::ldexp(1.0, e); }  // next power of two >= bound4
   BuildPlan& P = ctx->plan[S.attenuated ? 1 : 0];
-  DevBuf& d_km = ctx->d_rowsbuf;
+  DevBuf& d_km = P.d_km;
   int rc;
   double t_planned = tnow(), t_uploaded = t_planned;
   size_t km_count = 0;
@@ -764,12 +836,17 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     P.valid = false;
     P.chunks.clear(); P.cps.clear(); P.km_off.clear(); P.total_local = 0;
     std::vector<std::vector<int>> kmax_all;  // index by list pair order
+    // OQPB_ONLY="a,b": profiling knob, build only the (bra list a, ket list b) launches (list = class * 4 + bucket)
+    static const char* only_env = getenv("OQPB_ONLY");
+    int only_a = -1, only_b = -1;
+    if (only_env) sscanf(only_env, "%d,%d", &only_a, &only_b);
     for (int pca = 0; pca < NL; ++pca) {  // pca / pcb are pair LISTS here (class x contraction bucket)
       int na = T.cls_off[pca + 1] - T.cls_off[pca];
       if (na == 0) continue;
       for (int pcb = 0; pcb <= pca; ++pcb) {
         int nb = T.cls_off[pcb + 1] - T.cls_off[pcb];
         if (nb == 0) continue;
+        if (only_a >= 0 && (pca != only_a || pcb != only_b)) continue;
         const double* Qa = hQ.data() + T.cls_off[pca];
         std::vector<int> km(na, 0);
         // kets at or beyond km[p] cannot survive: suffix maxima of the ket list's bounds are monotone
@@ -826,12 +903,20 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   };
 
   size_t nch = chunks.size();
-  if ((rc = ensure_counts(ctx, 2 * nch + 2))) return rc;
-  CK(ctx->d_counters.ensure((3 * nch + 4) * sizeof(unsigned long long)));
-  CK(cudaMemsetAsync(ctx->d_counters.p, 0, (3 * nch + 4) * sizeof(unsigned long long), ctx->stream));
-  unsigned* d_cnt = ctx->d_counters.as<unsigned>();  // [2*c] = ntasks, [2*c+1] = fetch counter
+  if ((rc = ensure_counts(ctx, 4 * nch + 4))) return rc;
+  CK(ctx->d_counters.ensure((4 * nch + 4) * sizeof(unsigned)));
+  CK(cudaMemsetAsync(ctx->d_counters.p, 0, (4 * nch + 4) * sizeof(unsigned), ctx->stream));
+  unsigned* d_cnt = ctx->d_counters.as<unsigned>();  // [4*c] = ntasks, [4*c+1] = fetch counter, [4*c+2] = run items
   const int nlane = ctx->profile || ctx->record ? 1 : ctx->nlanes;
-  for (int l = 0; l < nlane; ++l) CK(ctx->d_tasks[l].ensure(ctx->task_cap * sizeof(int2)));
+  // run kernels (one Fock matrix, SYM consumers): warp items = pieces of RUN_LEN kets, at most one short piece per bra
+  const bool run_ok = ctx->use_run && S.mode == MODE_SYM && S.nmat == 1 && !ctx->record;
+  size_t max_list = 0;
+  for (int l = 0; l < NL; ++l) max_list = std::max<size_t>(max_list, T.cls_off[l + 1] - T.cls_off[l]);
+  const size_t item_cap = ctx->task_cap / RUN_LEN + max_list + 1;
+  for (int l = 0; l < nlane; ++l) {
+    CK(ctx->d_tasks[l].ensure(ctx->task_cap * sizeof(int2)));
+    if (run_ok) CK(ctx->d_items[l].ensure(item_cap * sizeof(int2)));
+  }
   CK(ctx->d_stats.ensure((2 * nch + 2) * sizeof(unsigned long long)));
   CK(cudaMemsetAsync(ctx->d_stats.p, 0, (2 * nch + 2) * sizeof(unsigned long long), ctx->stream));
   std::vector<unsigned long long> h_stats(2 * nch + 2, 0);
@@ -858,6 +943,14 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     const int ln = (int)(c % nlane);
     cudaStream_t cs = nlane > 1 ? ctx->lane[ln] : ctx->stream;
     int2* d_tasks = ctx->d_tasks[ln].as<int2>();
+    const int qcls = quartet_class(pc_of(ch.pca), pc_of(ch.pcb));
+    const ClassEntry& ce = tab[qcls];
+    // few, heavily contracted quartets (small molecules): warp per quartet, lanes over the primitive quartets
+    const bool wpq = ce.launch_wpq != nullptr && ch.cand <= ctx->wpq_max_tasks && (ch.pca % NBK >= 2 || ch.pcb % NBK >= 2);
+    // measured on (H2O)32/cc-pVTZ per contraction bucket pair: the run kernels win 9-10 % where both pairs have few
+    // primitives (buckets 0/1), are neutral at (0,2) / (2,0) / (1,1) and lose 7-40 % on the heavily contracted launches
+    const bool run = run_ok && !wpq && ce.launch_run != nullptr && (ch.pca % NBK) + (ch.pcb % NBK) <= ctx->run_max_bucket_sum;
+    int2* d_items = run ? ctx->d_items[ln].as<int2>() : nullptr;
     size_t ci = cp_index(ch.pca, ch.pcb);
     int offa = T.cls_off[ch.pca], offb = T.cls_off[ch.pcb];
     int nbra = (ch.p1 - ch.p0 + nr - 1) / nr + 1;
@@ -868,13 +961,18 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
         dQ + offb, ctx->d_d4.as<double>() + offa, ctx->d_d4.as<double>() + offb,
         ctx->d_ok.as<int>() + offa, ctx->d_ok.as<int>() + offb, T.d_canon.as<int>() + offa,
         T.d_canon.as<int>() + offb, d_km.as<int>() + km_off[ci], pstart, ch.p1, nr, ch.pca == ch.pcb,
-        ctx->d_dsh.as<double>(), ns, cutoff, d_tasks, d_cnt + 2 * c, (unsigned)ctx->task_cap, use_smem);
+        ctx->d_dsh.as<double>(), ns, cutoff, d_tasks, d_cnt + 4 * c, (unsigned)ctx->task_cap, use_smem, d_items,
+        d_cnt + 4 * c + 2, (unsigned)item_cap);
     CK(cudaGetLastError());
     EriArgs A;
     fill_common_args(ctx, T, ch.pca, ch.pcb, A);
     A.tasks = d_tasks;
-    A.ntasks = d_cnt + 2 * c;
-    A.counter = d_cnt + 2 * c + 1;
+    A.ntasks = d_cnt + 4 * c;
+    A.task_cap = (unsigned)ctx->task_cap;
+    A.counter = d_cnt + 4 * c + 1;
+    A.items = d_items;
+    A.nitems = d_cnt + 4 * c + 2;
+    A.item_cap = (unsigned)item_cap;
     A.prim_cutoff = ctx->cut.pair * ctx->cut.pair;
     A.cutoff = cutoff;
     A.mu2inv = S.attenuated ? 1.0 / (T.att_mu * T.att_mu) : 0.0;
@@ -885,15 +983,15 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     A.cj = S.cj; A.ck = S.ck;
     A.Pgen = S.Pgen; A.Fgen = S.Fgen; A.gen_nmat_total = S.gen_nm; A.gen_ncoul = S.gen_ncoul; A.gen_nvec = S.gen_nvec;
     A.gen_mcount = S.gen_mcount >= 0 ? S.gen_mcount : S.gen_nm;
-    const int qcls = quartet_class(pc_of(ch.pca), pc_of(ch.pcb));
-    const ClassEntry& ce = tab[qcls];
-    // few, heavily contracted quartets (small molecules): warp per quartet, lanes over the primitive quartets
-    const bool wpq = ce.launch_wpq != nullptr && ch.cand <= ctx->wpq_max_tasks && (ch.pca % NBK >= 2 || ch.pcb % NBK >= 2);
+    A.gen_xoff = S.gen_xoff;
     const size_t tasks_per_cta = wpq ? 4 : (size_t)ce.qpb;
+    // run kernels: a warp = an item; the item count is bounded by candidates / RUN_LEN + one per bra, a warp's mean load by
+    // the survivor count: size the grid like the task kernel's (one thread per candidate quartet)
     size_t nb = std::min<size_t>((ch.cand + tasks_per_cta - 1) / tasks_per_cta, (size_t)ce.maxcta * ctx->grid_pct / 100);
+    if (run) nb = std::min<size_t>(nb, (ch.cand / RUN_LEN + (size_t)nbra + ce.qpb / 32 - 1) / (ce.qpb / 32) + 1);
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (ctx->profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, cs); }
-    CK((wpq ? ce.launch_wpq : ce.launch)(A, (int)std::max<size_t>(nb, 1), cs));
+    CK((run ? ce.launch_run : (wpq ? ce.launch_wpq : ce.launch))(A, (int)std::max<size_t>(nb, 1), cs));
     if (ctx->profile) {
       cudaEventRecord(pe1, cs);
       cudaEventSynchronize(pe1);
@@ -906,7 +1004,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     ctx->st_launches += 2;
     if (ctx->record) {
       unsigned n = 0;
-      CK(cudaMemcpyAsync(&n, d_cnt + 2 * c, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemcpyAsync(&n, d_cnt + 4 * c, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
       rec_tmp.resize(n);
       CK(cudaMemcpy(rec_tmp.data(), d_tasks, n * sizeof(int2), cudaMemcpyDeviceToHost));
@@ -927,7 +1025,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   }
   const double t_launched = tnow();
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
-  if (nch) CK(cudaMemcpyAsync(ctx->h_counts, d_cnt, 2 * nch * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  if (nch) CK(cudaMemcpyAsync(ctx->h_counts, d_cnt, 4 * nch * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
   if (nch) CK(cudaMemcpyAsync(h_stats.data(), ctx->d_stats.p, 2 * nch * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   float ms = 0;
@@ -940,7 +1038,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   long long surv = 0;
   double flops = 0;
   for (size_t c = 0; c < nch; ++c) {
-    unsigned n = ctx->h_counts[2 * c];
+    unsigned n = ctx->h_counts[4 * c];
     if (n > ctx->task_cap) { ctx->err = "task buffer overflow"; return OQPB_ERR_STATE; }
     surv += n;
     // algorithmic FLOPs: primitive quartets past the int_rys.F90:232 test x F_prim(class)
@@ -959,7 +1057,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     // per-launch dump: pair list (class*4 + contraction bucket) of bra and ket, ms, quartets, primitive quartets
     if (FILE* fp = fopen(getenv("OQPB_PROF_FILE"), "a")) {
       for (size_t c = 0; c < nch; ++c)
-        fprintf(fp, "%d %d %.4f %u %llu\n", chunks[c].pca, chunks[c].pcb, chunk_ms[c], ctx->h_counts[2 * c],
+        fprintf(fp, "%d %d %.4f %u %llu\n", chunks[c].pca, chunks[c].pcb, chunk_ms[c], ctx->h_counts[4 * c],
                 (unsigned long long)h_stats[2 * c]);
       fclose(fp);
     }
@@ -981,6 +1079,79 @@ int check_ready(oqpb_ctx* ctx) {
 
 oqpb_ctx* g_default_ctx = nullptr;
 int g_default_urohf = -1;
+
+// ---- NCCL, loaded on demand: a host without NCCL (or with a single GPU) never needs it
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi* nccl_api(std::string& err) {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* names[] = {getenv("OQPB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      if (!n) continue;
+      api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.h) break;
+    }
+    if (api.h) {
+      api.CommInitAll = (decltype(api.CommInitAll))dlsym(api.h, "ncclCommInitAll");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.h, "ncclCommDestroy");
+      api.AllReduce = (decltype(api.AllReduce))dlsym(api.h, "ncclAllReduce");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.h, "ncclGetErrorString");
+    }
+  }
+  if (!api.h || !api.CommInitAll || !api.CommDestroy || !api.AllReduce) {
+    err = "NCCL not available (libnccl.so.2; set OQPB_NCCL_LIB)";
+    return nullptr;
+  }
+  return &api;
+}
+
+// member d of a multi-device context (0 = the master itself)
+inline oqpb_ctx* member(oqpb_ctx* ctx, int d) { return d == 0 ? ctx : ctx->peers[d - 1]; }
+
+// run fn(member, d) on one host thread per device (run_build blocks its host thread); first non-zero return wins
+template <class F>
+int for_each_member(oqpb_ctx* ctx, F&& fn) {
+  const int n = ctx->mndev;
+  std::vector<int> rc(n, 0);
+  std::vector<std::thread> th;
+  for (int d = 1; d < n; ++d) th.emplace_back([&, d] { rc[d] = fn(member(ctx, d), d); });
+  rc[0] = fn(ctx, 0);
+  for (auto& t : th) t.join();
+  for (int d = 0; d < n; ++d)
+    if (rc[d]) {
+      if (d > 0) ctx->err = "device " + std::to_string(member(ctx, d)->device) + ": " + member(ctx, d)->err;
+      return rc[d];
+    }
+  return OQPB_OK;
+}
+
+// sum the partial results of the members in place: ONE ncclAllReduce on each member's compute stream
+// (replaces pe%allreduce, int2.F90:1392-1397 / parallel.F90:429-440)
+int member_allreduce(oqpb_ctx* c, double* buf, size_t count) {
+  std::string err;
+  NcclApi* api = nccl_api(err);
+  if (!api) { c->err = err; return OQPB_ERR_STATE; }
+  ncclResult_t r = api->AllReduce(buf, buf, count, ncclDouble, ncclSum, c->comm, c->stream);
+  if (r != ncclSuccess) {
+    c->err = std::string("ncclAllReduce: ") + (api->GetErrorString ? api->GetErrorString(r) : "error");
+    return OQPB_ERR_CUDA;
+  }
+  return OQPB_OK;
+}
+
+void apply_partition(oqpb_ctx* c) {
+  c->rank = c->base_rank * c->mndev + c->mdev;
+  c->nranks = c->base_nranks * c->mndev;
+  ++c->plan_gen;
+}
 
 }  // namespace
 
@@ -1007,27 +1178,77 @@ int oqpb_ctx_create(oqpb_ctx** out, int device) {
   // tuning knobs (tools/sweep_knobs.sh)
   if (const char* e = getenv("OQPB_NLANES")) ctx->nlanes = std::max(1, std::min((int)oqpb_ctx::NSTREAM, atoi(e)));
   if (const char* e = getenv("OQPB_GRID_PCT")) ctx->grid_pct = std::max(10, atoi(e));
+  if (const char* e = getenv("OQPB_RUN")) ctx->use_run = atoi(e) != 0;
+  if (const char* e = getenv("OQPB_RUN_BUCKETS")) ctx->run_max_bucket_sum = atoi(e);
   if (const char* e = getenv("OQPB_WPQ_MAX")) ctx->wpq_max_tasks = (size_t)std::max(0, atoi(e));
   if (const char* e = getenv("OQPB_TASK_CAP_LOG2")) ctx->task_cap = (size_t)1 << std::max(16, std::min(28, atoi(e)));
-  // Rys tables
+  // Rys tables: the generated Chebyshev fits are converted to monomial coefficients (Horner evaluation in the kernels)
   if (ctx->d_rys.ensure(sizeof(RYS_TAB_H) + sizeof(RYSF_TAB_H)) != cudaSuccess) { delete ctx; return OQPB_ERR_CUDA; }
-  cudaMemcpy(ctx->d_rys.p, RYS_TAB_H, sizeof(RYS_TAB_H), cudaMemcpyHostToDevice);
-  cudaMemcpy(ctx->d_rys.as<double>() + RYS_NTAB, RYSF_TAB_H, sizeof(RYSF_TAB_H), cudaMemcpyHostToDevice);  // nroots 1, 2
+  {
+    std::vector<double> mono(RYS_NTAB + RYSF_NTAB);
+    cheb_to_monomial(RYS_TAB_H, RYS_NTAB, RYS_NCOEF, mono.data());
+    cheb_to_monomial(RYSF_TAB_H, RYSF_NTAB, RYSF_NCOEF, mono.data() + RYS_NTAB);  // nroots 1, 2: fine intervals
+    cudaMemcpy(ctx->d_rys.p, mono.data(), mono.size() * sizeof(double), cudaMemcpyHostToDevice);
+  }
   ctx->d_maxden.ensure(16);
   *out = ctx;
   return OQPB_OK;
 }
 
+// One context driving ndev GPUs of this node from a single process: replicated basis / pair table / Schwarz matrix /
+// density, the bra shell-pair list split over the devices (on top of the caller's rank split), partial results summed by
+// ONE ncclAllReduce on the compute streams.  Every host-pointer entry (oqpb_fock, oqpb_fock_cam, oqpb_jk_mrsf[_cam],
+// routec_fock_jk) then uses all the devices; a non-MPI OpenQP reaches GPUs 1..7 this way.
+int oqpb_ctx_create_multi(oqpb_ctx** out, int ndev, const int* devices) {
+  if (!out || ndev < 1) return OQPB_ERR_BAD_ARG;
+  *out = nullptr;
+  int have = 0;
+  if (cudaGetDeviceCount(&have) != cudaSuccess || have == 0) return OQPB_ERR_NO_DEVICE;
+  if (ndev > have) return OQPB_ERR_BAD_ARG;
+  std::vector<int> devs(ndev);
+  for (int d = 0; d < ndev; ++d) devs[d] = devices ? devices[d] : d;
+  std::vector<oqpb_ctx*> c(ndev, nullptr);
+  auto cleanup = [&] { for (oqpb_ctx* x : c) if (x) { x->peers.clear(); oqpb_ctx_destroy(x); } };
+  for (int d = 0; d < ndev; ++d) {
+    int rc = oqpb_ctx_create(&c[d], devs[d]);
+    if (rc) { cleanup(); return rc; }
+    c[d]->mdev = d;
+    c[d]->mndev = ndev;
+    apply_partition(c[d]);
+  }
+  if (ndev > 1) {
+    std::string err;
+    NcclApi* api = nccl_api(err);
+    std::vector<ncclComm_t> comms(ndev, nullptr);
+    if (!api || api->CommInitAll(comms.data(), ndev, devs.data()) != ncclSuccess) { cleanup(); return OQPB_ERR_STATE; }
+    for (int d = 0; d < ndev; ++d) c[d]->comm = comms[d];
+  }
+  for (int d = 1; d < ndev; ++d) c[0]->peers.push_back(c[d]);
+  cudaSetDevice(devs[0]);
+  *out = c[0];
+  return OQPB_OK;
+}
+
+int oqpb_ctx_ndevices(const oqpb_ctx* ctx) { return ctx ? ctx->mndev : 0; }
+
 void oqpb_ctx_destroy(oqpb_ctx* ctx) {
   if (!ctx) return;
+  for (oqpb_ctx* p : ctx->peers) oqpb_ctx_destroy(p);
+  ctx->peers.clear();
   cudaSetDevice(ctx->device);
+  if (ctx->comm) {
+    std::string err;
+    if (NcclApi* api = nccl_api(err)) api->CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+  }
   if (g_default_ctx == ctx) g_default_ctx = nullptr;
   free_pairtable(ctx->run);
   for (DevBuf* b : {&ctx->d_am, &ctx->d_ncontr, &ctx->d_goff, &ctx->d_aooff, &ctx->d_naos, &ctx->d_ex, &ctx->d_cc,
                     &ctx->d_xyz, &ctx->d_rys, &ctx->d_Qmat, &ctx->d_dsh, &ctx->d_maxden, &ctx->d_ok,
-                    &ctx->d_d4, &ctx->d_rowsbuf, &ctx->d_tasks[0], &ctx->d_tasks[1], &ctx->d_tasks[2], &ctx->d_tasks[3], &ctx->d_counters, &ctx->d_Dsq, &ctx->d_F, &ctx->d_Din,
-                    &ctx->d_stats, &ctx->d_gen_in, &ctx->d_gen_out})
+                    &ctx->d_d4, &ctx->d_rowsbuf, &ctx->plan[0].d_km, &ctx->plan[1].d_km, &ctx->d_counters, &ctx->d_Dsq, &ctx->d_F, &ctx->d_Din,
+                    &ctx->d_stats, &ctx->d_gen_in, &ctx->d_gen_out, &ctx->d_mask})
     b->release();
+  for (int l = 0; l < oqpb_ctx::NSTREAM; ++l) { ctx->d_tasks[l].release(); ctx->d_items[l].release(); }
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
@@ -1077,11 +1298,20 @@ int oqpb_set_basis(oqpb_ctx* ctx, int nshell, int nprim, const int* am, const in
   ctx->have_basis = true;
   ctx->have_cutoff = ctx->have_screen = false;
   ++ctx->plan_gen;
+  for (oqpb_ctx* pr : ctx->peers) {  // multi-device context: replicate
+    rc = oqpb_set_basis(pr, nshell, nprim, am, harmonic, ncontr, g_offset, ao_offset, naos, ex, cc, centers, harmonic_active);
+    if (rc) { ctx->err = pr->err; return rc; }
+  }
+  cudaSetDevice(ctx->device);
   return OQPB_OK;
 }
 
 int oqpb_set_cutoff(oqpb_ctx* ctx, double cutoff) {
   if (!ctx || !ctx->have_basis) return OQPB_ERR_STATE;
+  for (oqpb_ctx* pr : ctx->peers) {
+    int rcp = oqpb_set_cutoff(pr, cutoff);
+    if (rcp) { ctx->err = pr->err; return rcp; }
+  }
   cudaSetDevice(ctx->device);
   ctx->cutoff = cutoff;
   ctx->cut = Cutoffs{cutoff, 1.0e-2 * cutoff, 1.0e-4 * cutoff, 25.0 * std::log(10.0)};  // int2.F90:260-272
@@ -1109,6 +1339,11 @@ int oqpb_set_screening(oqpb_ctx* ctx, const double* schwarz_in) {
   CK(ctx->d_dsh.ensure((size_t)ns * ns * sizeof(double)));
   ctx->have_screen = true;
   ++ctx->plan_gen;
+  for (oqpb_ctx* pr : ctx->peers) {  // the Schwarz matrix is computed once and replicated
+    rc = oqpb_set_screening(pr, ctx->Qmat.data());
+    if (rc) { ctx->err = pr->err; return rc; }
+  }
+  cudaSetDevice(ctx->device);
   return OQPB_OK;
 }
 
@@ -1134,6 +1369,11 @@ int oqpb_set_screening_cam(oqpb_ctx* ctx, double mu, const double* schwarz_att_i
   if ((rc = upload(ctx, T.d_Qatt, T.Qatt))) return rc;
   T.att_mu = mu;
   ctx->plan[1].valid = false;
+  for (oqpb_ctx* pr : ctx->peers) {
+    rc = oqpb_set_screening_cam(pr, mu, ctx->Qmat_att.data());
+    if (rc) { ctx->err = pr->err; return rc; }
+  }
+  cudaSetDevice(ctx->device);
   return OQPB_OK;
 }
 
@@ -1149,11 +1389,34 @@ int oqpb_get_schwarz(oqpb_ctx* ctx, double* out) {
   return OQPB_OK;
 }
 
+// Restrict the builds to the quartets whose reference bra pair (the canonically larger shell pair of the quartet,
+// int2.F90:756-780) is flagged in mask[i(i+1)/2 + j] (0-based, i >= j); NULL removes the restriction.  Used to
+// compare a sample of a large build with the oracle run on the same bra subset.
+int oqpb_set_bra_mask(oqpb_ctx* ctx, const unsigned char* mask, long long npairs) {
+  if (!ctx || !ctx->have_basis) return OQPB_ERR_STATE;
+  cudaSetDevice(ctx->device);
+  for (oqpb_ctx* pr : ctx->peers) {
+    int rcp = oqpb_set_bra_mask(pr, mask, npairs);
+    if (rcp) return rcp;
+  }
+  cudaSetDevice(ctx->device);
+  if (!mask) { ctx->have_mask = false; return OQPB_OK; }
+  if (npairs != (long long)ctx->nshell * (ctx->nshell + 1) / 2) return OQPB_ERR_BAD_ARG;
+  CK(ctx->d_mask.ensure((size_t)npairs));
+  CK(cudaMemcpy(ctx->d_mask.p, mask, (size_t)npairs, cudaMemcpyHostToDevice));
+  ctx->have_mask = true;
+  return OQPB_OK;
+}
+
 int oqpb_set_partition(oqpb_ctx* ctx, int rank, int nranks) {
   if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return OQPB_ERR_BAD_ARG;
-  ctx->rank = rank;
-  ++ctx->plan_gen;
-  ctx->nranks = nranks;
+  // a multi-device context splits the caller's slice once more over its devices
+  for (int d = 0; d < ctx->mndev; ++d) {
+    oqpb_ctx* c = member(ctx, d);
+    c->base_rank = rank;
+    c->base_nranks = nranks;
+    apply_partition(c);
+  }
   return OQPB_OK;
 }
 
@@ -1245,43 +1508,52 @@ int oqpb_set_stream(oqpb_ctx* ctx, void* stream) {
   return OQPB_OK;
 }
 
-int oqpb_fock(oqpb_ctx* ctx, int urohf, const double* d, double* f, int nfocks, double se, double sc, int post,
-              long long* nskipped) {
+// Host-pointer Fock build on every member of the context: H2D of the packed densities, the member's slice of the
+// build, (multi-device) ONE ncclAllReduce of the packed partial Fock matrices on the compute streams, post-scaling
+// and D2H on the master.
+static int fock_host(oqpb_ctx* ctx, int urohf, const double* d, double* f, int nfocks, int npass, const double* se,
+                     const double* sc, double mu, int post, long long* nskipped) {
   int rc = check_ready(ctx);
   if (rc) return rc;
-  cudaSetDevice(ctx->device);
+  if (npass == 2 && (rc = oqpb_set_screening_cam(ctx, mu, nullptr))) return rc;  // no-op when cached for this mu
   const long ntri = (long)ctx->nbf * (ctx->nbf + 1) / 2;
-  size_t bytes = (size_t)nfocks * ntri * sizeof(double);
-  CK(ctx->d_Din.ensure(bytes));
-  CK(ctx->d_F.ensure(bytes));
-  CK(cudaMemcpyAsync(ctx->d_Din.p, d, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  rc = oqpb_fock_dev(ctx, urohf, ctx->d_Din.as<double>(), ctx->d_F.as<double>(), nfocks, se, sc);
+  const size_t bytes = (size_t)nfocks * ntri * sizeof(double);
+  auto body = [&](oqpb_ctx* c, int dev) -> int {
+    oqpb_ctx* ctx = c;  // CK reports into the member
+    cudaSetDevice(c->device);
+    CK(c->d_Din.ensure(bytes));
+    CK(c->d_F.ensure(bytes));
+    CK(cudaMemcpyAsync(c->d_Din.p, d, bytes, cudaMemcpyHostToDevice, c->stream));
+    int r = fock_core(c, urohf, c->d_Din.as<double>(), c->d_F.as<double>(), nfocks, npass, se, sc);
+    if (r) return r;
+    if (c->mndev > 1 && (r = member_allreduce(c, c->d_F.as<double>(), (size_t)nfocks * ntri))) return r;
+    if (dev == 0) {
+      if (post && (r = oqpb_fock_post_dev(c, c->d_F.as<double>(), nfocks))) return r;
+      CK(cudaMemcpyAsync(f, c->d_F.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return OQPB_OK;
+  };
+  rc = ctx->mndev > 1 ? for_each_member(ctx, body) : body(ctx, 0);
   if (rc) return rc;
-  if (post) { rc = oqpb_fock_post_dev(ctx, ctx->d_F.as<double>(), nfocks); if (rc) return rc; }
-  CK(cudaMemcpyAsync(f, ctx->d_F.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  for (oqpb_ctx* pr : ctx->peers) {  // whole-context statistics
+    ctx->st_survivors += pr->st_survivors; ctx->st_skipped += pr->st_skipped; ctx->st_flops += pr->st_flops;
+    ctx->st_launches += pr->st_launches; ctx->st_kernel_ms = std::max(ctx->st_kernel_ms, pr->st_kernel_ms);
+  }
+  cudaSetDevice(ctx->device);
   if (nskipped) *nskipped = ctx->st_skipped;
   return OQPB_OK;
 }
 
+int oqpb_fock(oqpb_ctx* ctx, int urohf, const double* d, double* f, int nfocks, double se, double sc, int post,
+              long long* nskipped) {
+  return fock_host(ctx, urohf, d, f, nfocks, 1, &se, &sc, 0.0, post, nskipped);
+}
+
 int oqpb_fock_cam(oqpb_ctx* ctx, int urohf, const double* d, double* f, int nfocks, double alpha, double beta, double mu,
                   double alpha_coulomb, double beta_coulomb, int post, long long* nskipped) {
-  int rc = check_ready(ctx);
-  if (rc) return rc;
-  cudaSetDevice(ctx->device);
-  const long ntri = (long)ctx->nbf * (ctx->nbf + 1) / 2;
-  size_t bytes = (size_t)nfocks * ntri * sizeof(double);
-  CK(ctx->d_Din.ensure(bytes));
-  CK(ctx->d_F.ensure(bytes));
-  CK(cudaMemcpyAsync(ctx->d_Din.p, d, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  rc = oqpb_fock_cam_dev(ctx, urohf, ctx->d_Din.as<double>(), ctx->d_F.as<double>(), nfocks, alpha, beta, mu, alpha_coulomb,
-                         beta_coulomb);
-  if (rc) return rc;
-  if (post) { rc = oqpb_fock_post_dev(ctx, ctx->d_F.as<double>(), nfocks); if (rc) return rc; }
-  CK(cudaMemcpyAsync(f, ctx->d_F.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  if (nskipped) *nskipped = ctx->st_skipped;
-  return OQPB_OK;
+  const double se[2] = {alpha, beta}, sc[2] = {alpha_coulomb, beta_coulomb};
+  return fock_host(ctx, urohf, d, f, nfocks, 2, se, sc, mu, post, nskipped);
 }
 
 // shared driver for the general-density consumers: X interleaved [(nu*nbf+mu)*NM + m]
@@ -1308,6 +1580,12 @@ static int td_core(oqpb_ctx* ctx, const double* d2, int nvec, int flags, int npa
   if (npass == 2 && (rc = oqpb_set_screening_cam(ctx, mu, nullptr))) return rc;
   const double se = sev[0], sc = scv[0];
   if (nvec < 1) return OQPB_ERR_BAD_ARG;
+  // multi-device context: the TD consumer is not split over the devices yet -- the master does this rank's whole slice
+  struct WholeSlice {
+    oqpb_ctx* c;
+    explicit WholeSlice(oqpb_ctx* x) : c(x) { if (c->mndev > 1) { c->rank = c->base_rank; c->nranks = c->base_nranks; ++c->plan_gen; } }
+    ~WholeSlice() { if (c->mndev > 1) apply_partition(c); }
+  } whole(ctx);
   const int ns = ctx->nshell, nbf = ctx->nbf;
   const long n2 = (long)nbf * nbf, npairs = (long)ns * (ns + 1) / 2;
   const bool tda = flags & OQPB_TD_TDA;
@@ -1432,18 +1710,31 @@ static int mrsf_host(oqpb_ctx* ctx, const double* d3, int nvec, int ncomp, doubl
                      long long* nskipped, int npass, double se2, double mu) {
   int rc = check_ready(ctx);
   if (rc) return rc;
-  cudaSetDevice(ctx->device);
   if (nvec < 1 || ncomp < 4) return OQPB_ERR_BAD_ARG;
+  if (npass == 2 && (rc = oqpb_set_screening_cam(ctx, mu, nullptr))) return rc;
   const long n2 = (long)ctx->nbf * ctx->nbf;
   const int NM = nvec * ncomp;
-  size_t bytes = (size_t)n2 * NM * sizeof(double);
-  CK(ctx->d_gen_in.ensure(bytes));
-  CK(ctx->d_gen_out.ensure(bytes));
-  CK(cudaMemcpyAsync(ctx->d_gen_in.p, d3, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  rc = mrsf_core(ctx, ctx->d_gen_in.as<double>(), ctx->d_gen_out.as<double>(), nvec, ncomp, se, sc, npass, se2, mu);
+  const size_t bytes = (size_t)n2 * NM * sizeof(double);
+  auto body = [&](oqpb_ctx* c, int dev) -> int {
+    oqpb_ctx* ctx = c;
+    cudaSetDevice(c->device);
+    CK(c->d_gen_in.ensure(bytes));
+    CK(c->d_gen_out.ensure(bytes));
+    CK(cudaMemcpyAsync(c->d_gen_in.p, d3, bytes, cudaMemcpyHostToDevice, c->stream));
+    int r = mrsf_core(c, c->d_gen_in.as<double>(), c->d_gen_out.as<double>(), nvec, ncomp, se, sc, npass, se2, mu);
+    if (r) return r;
+    if (c->mndev > 1 && (r = member_allreduce(c, c->d_gen_out.as<double>(), (size_t)n2 * NM))) return r;
+    if (dev == 0) CK(cudaMemcpyAsync(f3, c->d_gen_out.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return OQPB_OK;
+  };
+  rc = ctx->mndev > 1 ? for_each_member(ctx, body) : body(ctx, 0);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(f3, ctx->d_gen_out.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  for (oqpb_ctx* pr : ctx->peers) {
+    ctx->st_survivors += pr->st_survivors; ctx->st_skipped += pr->st_skipped; ctx->st_flops += pr->st_flops;
+    ctx->st_launches += pr->st_launches; ctx->st_kernel_ms = std::max(ctx->st_kernel_ms, pr->st_kernel_ms);
+  }
+  cudaSetDevice(ctx->device);
   if (nskipped) *nskipped = ctx->st_skipped;
   return OQPB_OK;
 }
@@ -1455,6 +1746,259 @@ int oqpb_jk_mrsf(oqpb_ctx* ctx, const double* d3, int nvec, int ncomp, double se
 int oqpb_jk_mrsf_cam(oqpb_ctx* ctx, const double* d3, int nvec, int ncomp, double alpha, double beta, double mu,
                      double alpha_coulomb, double* f3, long long* nskipped) {
   return mrsf_host(ctx, d3, nvec, ncomp, alpha, alpha_coulomb, f3, nskipped, 2, beta, mu);
+}
+
+// ---- generic J/K engine on the GEN path (oqpb_jk) and the response / gradient consumers built on it ----------
+namespace {
+struct Slab { const double* src; int op; };  // host column-major nbf x nbf matrix and the k_slab_pack operation
+// Upload `mats` (host, nbf^2 each), screen on them exactly like shltd / shlrpagrd (tdhf_lib.F90:300-325, 1324-1350:
+// dsh(I,J) = max |P(mu in J, nu in I)| over all matrices, I >= J), then build  X_m = sum of its slabs'  op(P)  and run ONE
+// GEN build:  Fgen_m = cj * J[X_m] (m < ncoul)  -  ck * K[X_m] (m >= ncoul).   J[P](a,b) = sum_cd (ab|cd) P(c,d),
+// K[P](a,c) = sum_bd (ab|cd) P(b,d).  Results stay in ctx->d_gen_out (interleaved, NM slabs).
+int jk_slabs(oqpb_ctx* ctx, const std::vector<const double*>& mats, const std::vector<std::vector<Slab>>& jslabs,
+             const std::vector<std::vector<Slab>>& kslabs, double cj, double ck, double flops_per_int) {
+  const int nbf = ctx->nbf, ns = ctx->nshell;
+  const long n2 = (long)nbf * nbf, npairs = (long)ns * (ns + 1) / 2;
+  const int nin = (int)mats.size(), nJ = (int)jslabs.size(), nK = (int)kslabs.size(), NM = nJ + nK;
+  if (nin < 1 || NM < 1) return OQPB_ERR_BAD_ARG;
+  const unsigned gb = (unsigned)((n2 + 255) / 256);
+  CK(ctx->d_Din.ensure((size_t)n2 * nin * sizeof(double)));
+  CK(ctx->d_gen_in.ensure((size_t)n2 * std::max(NM, nin) * sizeof(double)));
+  CK(ctx->d_gen_out.ensure((size_t)n2 * std::max(NM, nin) * sizeof(double)));
+  std::vector<const double*> dev(nin);
+  for (int q = 0; q < nin; ++q) {
+    dev[q] = ctx->d_Din.as<double>() + (size_t)q * n2;
+    CK(cudaMemcpyAsync((void*)dev[q], mats[q], (size_t)n2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    k_slab_pack<<<gb, 256, 0, ctx->stream>>>(dev[q], ctx->d_gen_out.as<double>(), nbf, nin, q, 0, 0);  // plain copy for screening
+  }
+  CK(cudaMemsetAsync(ctx->d_maxden.p, 0, 8, ctx->stream));
+  k_shlden_gen<<<(unsigned)((npairs + 127) / 128), 128, 0, ctx->stream>>>(
+      ns, npairs, ctx->d_aooff.as<int>(), ctx->d_naos.as<int>(), ctx->d_gen_out.as<double>(), nin, nbf, ctx->d_dsh.as<double>(),
+      ctx->d_maxden.as<unsigned long long>());
+  CK(cudaGetLastError());
+  auto index_of = [&](const double* p) { for (int q = 0; q < nin; ++q) if (mats[q] == p) return q; return -1; };
+  for (int m = 0; m < NM; ++m) {
+    const std::vector<Slab>& sl = m < nJ ? jslabs[m] : kslabs[m - nJ];
+    for (size_t t = 0; t < sl.size(); ++t) {
+      int q = index_of(sl[t].src);
+      if (q < 0) return OQPB_ERR_BAD_ARG;
+      k_slab_pack<<<gb, 256, 0, ctx->stream>>>(dev[q], ctx->d_gen_in.as<double>(), nbf, NM, m, sl[t].op, t > 0);
+    }
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemsetAsync(ctx->d_gen_out.p, 0, (size_t)n2 * NM * sizeof(double), ctx->stream));
+  BuildSpec S;
+  S.mode = MODE_GEN;
+  S.Pgen = ctx->d_gen_in.as<double>();
+  S.Fgen = ctx->d_gen_out.as<double>();
+  S.gen_nm = NM; S.gen_ncoul = nJ; S.gen_nvec = 1; S.gen_xoff = nJ; S.gen_mcount = nK;
+  S.cj = nJ > 0 ? cj : 0.0; S.ck = nK > 0 ? ck : 0.0;
+  S.digest_flops_per_int = flops_per_int;
+  return run_build(ctx, S);
+}
+// out (host) = sum_t scale_t * slab m_t of d_gen_out
+int jk_fetch(oqpb_ctx* ctx, int NM, const std::vector<std::pair<int, double>>& terms, double* out) {
+  const int nbf = ctx->nbf;
+  const long n2 = (long)nbf * nbf;
+  CK(ctx->d_F.ensure((size_t)n2 * sizeof(double)));
+  for (size_t t = 0; t < terms.size(); ++t)
+    k_slab_unpack<<<(unsigned)((n2 + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_gen_out.as<double>(), ctx->d_F.as<double>(), nbf, NM,
+                                                                         terms[t].first, terms[t].second, t > 0);
+  if (terms.empty()) CK(cudaMemsetAsync(ctx->d_F.p, 0, (size_t)n2 * sizeof(double), ctx->stream));
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, ctx->d_F.p, (size_t)n2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return OQPB_OK;
+}
+// a multi-device context runs these consumers on its first device over this rank's whole slice
+struct WholeSliceGuard {
+  oqpb_ctx* c;
+  explicit WholeSliceGuard(oqpb_ctx* x) : c(x) { if (c->mndev > 1) { c->rank = c->base_rank; c->nranks = c->base_nranks; ++c->plan_gen; } }
+  ~WholeSliceGuard() { if (c->mndev > 1) apply_partition(c); }
+};
+}  // namespace
+
+// Generic J/K for n general (non-symmetric) AO matrices P_m, column-major (nbf, nbf, n):
+//   J_m(a,b) = sum_cd (ab|cd) P_m(c,d)  if want_j[m],   K_m(a,c) = sum_bd (ab|cd) P_m(b,d)  if want_k[m]
+// (slabs of J / K that are not wanted are left untouched).  Screening density = max |P_m| per shell block over all m, the
+// rule of shltd (tdhf_lib.F90:300-325).  Every J/K consumer of the reference is a linear combination of these.
+int oqpb_jk(oqpb_ctx* ctx, int n, const double* P, const int* want_j, const int* want_k, double* J, double* K,
+            long long* nskipped) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (n < 1 || !P || !want_j || !want_k) return OQPB_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  WholeSliceGuard whole(ctx);
+  const size_t n2 = (size_t)ctx->nbf * ctx->nbf;
+  std::vector<const double*> mats(n);
+  std::vector<std::vector<Slab>> js, ks;
+  std::vector<int> jm, km;
+  for (int m = 0; m < n; ++m) {
+    mats[m] = P + m * n2;
+    if (want_j[m]) { js.push_back({Slab{mats[m], 0}}); jm.push_back(m); }
+    if (want_k[m]) { ks.push_back({Slab{mats[m], 0}}); km.push_back(m); }
+  }
+  if (js.empty() && ks.empty()) return OQPB_ERR_BAD_ARG;
+  if ((rc = jk_slabs(ctx, mats, js, ks, 1.0, 1.0, 4.0 * js.size() + 16.0 * ks.size()))) return rc;
+  const int NM = (int)(js.size() + ks.size());
+  for (size_t t = 0; t < jm.size(); ++t)
+    if ((rc = jk_fetch(ctx, NM, {{(int)t, 1.0}}, J + jm[t] * n2))) return rc;
+  for (size_t t = 0; t < km.size(); ++t)
+    if ((rc = jk_fetch(ctx, NM, {{(int)(js.size() + t), -1.0}}, K + km[t] * n2))) return rc;
+  if (nskipped) *nskipped = ctx->st_skipped;
+  return OQPB_OK;
+}
+
+// int2_tdgrd_data_t (tdhf_lib.F90:33-36, update :228-295, stop-time symmetrisation :107-109): two spin blocks
+// d2(nbf,nbf,2);  apb_s = 2 sc J[P_1 + P_2] - se K[P_s + P_s^T]  (s = 1, 2),  amb_1 = se K[P_1^T - P_1],  amb_2 = 0.
+int oqpb_jk_tdgrd(oqpb_ctx* ctx, const double* d2, int flags, double se, double sc, double* apb, double* amb,
+                  long long* nskipped) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!d2) return OQPB_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  WholeSliceGuard whole(ctx);
+  const size_t n2 = (size_t)ctx->nbf * ctx->nbf;
+  const bool want_apb = flags & OQPB_TD_APB, want_amb = flags & OQPB_TD_AMB;
+  if (!want_apb && !want_amb) return OQPB_ERR_BAD_ARG;
+  const double *P1 = d2, *P2 = d2 + n2;
+  std::vector<std::vector<Slab>> js, ks;
+  if (want_apb) {
+    js.push_back({Slab{P1, 0}, Slab{P2, 0}});
+    ks.push_back({Slab{P1, 1}});
+    ks.push_back({Slab{P2, 1}});
+  }
+  if (want_amb) ks.push_back({Slab{P1, 2}});
+  if ((rc = jk_slabs(ctx, {P1, P2}, js, ks, 1.0, 1.0, 4.0 * js.size() + 16.0 * ks.size()))) return rc;
+  const int NM = (int)(js.size() + ks.size());
+  if (want_apb && apb) {
+    if ((rc = jk_fetch(ctx, NM, {{0, 2.0 * sc}, {1, se}}, apb))) return rc;      // slabs hold +J and -K
+    if ((rc = jk_fetch(ctx, NM, {{0, 2.0 * sc}, {2, se}}, apb + n2))) return rc;
+  }
+  if (amb) {
+    if (want_amb) { if ((rc = jk_fetch(ctx, NM, {{NM - 1, -se}}, amb))) return rc; }
+    else memset(amb, 0, n2 * sizeof(double));
+    memset(amb + n2, 0, n2 * sizeof(double));
+  }
+  if (nskipped) *nskipped = ctx->st_skipped;
+  return OQPB_OK;
+}
+
+// int2_rpagrd_data_t (tdhf_lib.F90:42-57, 1068-1320): xpy, t -> H+ ; xmy -> H- ; arrays (nbf, nbf, nspin, n) column-major.
+//   nspin = 1:  H+[V] = 4 sc J[V] - 2 se K[V]           (V symmetric, as every caller passes it: the reference reads only
+//                                                        one triangle of V in the Coulomb term and is order-dependent otherwise)
+//   nspin = 2:  H+[V]_s = 2 sc J[V_1 + V_2] - se K[V_s + V_s^T]
+//   H-[V] = se K[V_1^T - V_1]  (first spin block only, as written :1297-1318; the other block stays zero)
+int oqpb_jk_rpagrd(oqpb_ctx* ctx, int nspin, int np, int nm, int nt, const double* xpy, const double* xmy, const double* t,
+                   double se, double sc, double* hpp, double* hpt, double* hmm, long long* nskipped) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if ((nspin != 1 && nspin != 2) || np < 0 || nm < 0 || nt < 0 || np + nm + nt == 0) return OQPB_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  WholeSliceGuard whole(ctx);
+  const size_t n2 = (size_t)ctx->nbf * ctx->nbf, slab = n2 * nspin;
+  std::vector<const double*> mats;
+  std::vector<std::vector<Slab>> js, ks;
+  struct Out { double* dst; std::vector<std::pair<int, double>> terms; };
+  std::vector<Out> outs;
+  std::vector<std::pair<int, int>> pending;  // (index into outs, k-slab ordinal) resolved once nJ is known
+  std::vector<int> pend_j;
+  auto add_plus = [&](const double* v, int cnt, double* dst) {
+    for (int q = 0; q < cnt; ++q) {
+      const double* v1 = v + q * slab;
+      for (int s2 = 0; s2 < nspin; ++s2) mats.push_back(v1 + s2 * n2);
+      if (nspin == 1) {
+        js.push_back({Slab{v1, 0}});
+        ks.push_back({Slab{v1, 0}});
+        outs.push_back({dst + q * slab, {{(int)js.size() - 1, 4.0 * sc}}});
+        pending.push_back({(int)outs.size() - 1, (int)ks.size() - 1});
+        pend_j.push_back(2);  // coefficient code: -2 se K  ->  slab holds -K: + 2 se
+      } else {
+        js.push_back({Slab{v1, 0}, Slab{v1 + n2, 0}});
+        for (int s2 = 0; s2 < 2; ++s2) {
+          ks.push_back({Slab{v1 + s2 * n2, 1}});
+          outs.push_back({dst + q * slab + s2 * n2, {{(int)js.size() - 1, 2.0 * sc}}});
+          pending.push_back({(int)outs.size() - 1, (int)ks.size() - 1});
+          pend_j.push_back(1);  // + se * slab
+        }
+      }
+    }
+  };
+  add_plus(xpy, np, hpp);
+  add_plus(t, nt, hpt);
+  for (int q = 0; q < nm; ++q) {
+    const double* v1 = xmy + q * slab;
+    for (int s2 = 0; s2 < nspin; ++s2) mats.push_back(v1 + s2 * n2);
+    ks.push_back({Slab{v1, 2}});
+    outs.push_back({hmm + q * slab, {}});
+    pending.push_back({(int)outs.size() - 1, (int)ks.size() - 1});
+    pend_j.push_back(-1);  // se K[V^T - V]: slab holds -K -> - se
+    if (nspin == 2) outs.push_back({hmm + q * slab + n2, {}});  // stays zero
+  }
+  const int nJ = (int)js.size();
+  for (size_t k = 0; k < pending.size(); ++k)
+    outs[pending[k].first].terms.push_back({nJ + pending[k].second, pend_j[k] == 2 ? 2.0 * se : (pend_j[k] == 1 ? se : -se)});
+  if ((rc = jk_slabs(ctx, mats, js, ks, 1.0, 1.0, 4.0 * js.size() + 16.0 * ks.size()))) return rc;
+  const int NM = nJ + (int)ks.size();
+  for (const Out& o : outs)
+    if ((rc = jk_fetch(ctx, NM, o.terms, o.dst))) return rc;
+  if (nskipped) *nskipped = ctx->st_skipped;
+  return OQPB_OK;
+}
+
+// int2_umrsf_data_t (tdhf_mrsf_lib.F90:28-32, update :337-426): d3, f3 (nvec, 11, nbf, nbf), nvec fastest.
+//   c = 1..8:  f3 = sc J[d3] - se K[d3];   c = 9, 10:  f3 = - se K[d3^T] (the mixed-spin permutation);   c = 11:  f3 = - se K[d3]
+// npass = 2 (int2_run_cam): pass 2 = Erf-attenuated exchange of component 11 only with `beta`.
+static int umrsf_core(oqpb_ctx* ctx, const double* d3, int nvec, double se, double sc, double* f3, long long* nskipped,
+                      int npass, double se2, double mu) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (nvec < 1 || !d3 || !f3) return OQPB_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  if (npass == 2 && (rc = oqpb_set_screening_cam(ctx, mu, nullptr))) return rc;
+  WholeSliceGuard whole(ctx);
+  const int nbf = ctx->nbf, ns = ctx->nshell, ncomp = 11, NM = nvec * ncomp;
+  const long n2 = (long)nbf * nbf, npairs = (long)ns * (ns + 1) / 2;
+  const size_t bytes = (size_t)n2 * NM * sizeof(double);
+  CK(ctx->d_Din.ensure(bytes));
+  CK(ctx->d_gen_in.ensure(bytes));
+  CK(ctx->d_gen_out.ensure(bytes));
+  CK(cudaMemcpyAsync(ctx->d_Din.p, d3, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  // screening on the caller's d3 (shell_den_screen_mrsf, tdhf_mrsf_lib.F90:189-214), before components 9/10 are transposed
+  CK(cudaMemsetAsync(ctx->d_maxden.p, 0, 8, ctx->stream));
+  k_shlden_gen<<<(unsigned)((npairs + 127) / 128), 128, 0, ctx->stream>>>(
+      ns, npairs, ctx->d_aooff.as<int>(), ctx->d_naos.as<int>(), ctx->d_Din.as<double>(), NM, nbf, ctx->d_dsh.as<double>(),
+      ctx->d_maxden.as<unsigned long long>());
+  k_umrsf_prepare<<<(unsigned)(((size_t)n2 * NM + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_Din.as<double>(), ctx->d_gen_in.as<double>(),
+                                                                                     nbf, nvec, ncomp);
+  CK(cudaGetLastError());
+  CK(cudaMemsetAsync(ctx->d_gen_out.p, 0, bytes, ctx->stream));
+  BuildSpec S;
+  S.mode = MODE_GEN;
+  S.Pgen = ctx->d_gen_in.as<double>();
+  S.Fgen = ctx->d_gen_out.as<double>();
+  S.gen_nm = NM; S.gen_ncoul = 8; S.gen_nvec = nvec;
+  S.cj = sc; S.ck = se;
+  S.digest_flops_per_int = (8.0 * 4 + 8.0 * 11) * 2 * nvec;
+  if ((rc = run_build(ctx, S))) return rc;
+  if (npass == 2) {
+    S.attenuated = true;
+    S.gen_ncoul = 0; S.gen_xoff = 10 * nvec; S.gen_mcount = nvec;
+    S.cj = 0.0; S.ck = se2;
+    S.digest_flops_per_int = 16.0 * nvec;
+    if ((rc = run_build(ctx, S))) return rc;
+  }
+  CK(cudaMemcpyAsync(f3, ctx->d_gen_out.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (nskipped) *nskipped = ctx->st_skipped;
+  return OQPB_OK;
+}
+int oqpb_jk_umrsf(oqpb_ctx* ctx, const double* d3, int nvec, double se, double sc, double* f3, long long* nskipped) {
+  return umrsf_core(ctx, d3, nvec, se, sc, f3, nskipped, 1, 0.0, 0.0);
+}
+int oqpb_jk_umrsf_cam(oqpb_ctx* ctx, const double* d3, int nvec, double alpha, double beta, double mu, double alpha_coulomb,
+                      double* f3, long long* nskipped) {
+  return umrsf_core(ctx, d3, nvec, alpha, alpha_coulomb, f3, nskipped, 2, beta, mu);
 }
 
 int oqpb_last_stats(oqpb_ctx* ctx, long long* s) {

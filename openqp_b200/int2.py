@@ -61,9 +61,14 @@ def _ip(a):
 class Int2Compute:
     """int2_compute_t (int2.F90:137-185)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, ndevices: int = 1):
+        """ndevices > 1: one context over GPUs 0 .. ndevices-1 of this node (oqpb_ctx_create_multi): the host-pointer
+        entries split the work over the devices and sum the partial results with one NCCL all-reduce"""
         self._h = C.c_void_p()
-        rc = lib().oqpb_ctx_create(C.byref(self._h), C.c_int(device))
+        if ndevices > 1:
+            rc = lib().oqpb_ctx_create_multi(C.byref(self._h), C.c_int(ndevices), None)
+        else:
+            rc = lib().oqpb_ctx_create(C.byref(self._h), C.c_int(device))
         if rc != 0:
             self._h = C.c_void_p()
             raise Int2Error(f"oqpb_ctx_create failed: {_ERRORS.get(rc, rc)} (this library has no CPU fallback)")
@@ -111,6 +116,14 @@ class Int2Compute:
 
     def set_partition(self, rank: int, nranks: int):
         self._check(lib().oqpb_set_partition(self._h, C.c_int(rank), C.c_int(nranks)), "oqpb_set_partition")
+
+    def set_bra_mask(self, mask=None):
+        """test hook (oqpb_set_bra_mask): restrict builds to quartets whose reference bra pair is flagged"""
+        if mask is None:
+            self._check(lib().oqpb_set_bra_mask(self._h, None, C.c_longlong(0)), "oqpb_set_bra_mask")
+        else:
+            m = np.ascontiguousarray(mask, dtype=np.uint8)
+            self._check(lib().oqpb_set_bra_mask(self._h, m.ctypes.data_as(C.c_void_p), C.c_longlong(m.size)), "oqpb_set_bra_mask")
 
     def set_screening_cam(self, mu: float, schwarz_att=None):
         """Schwarz matrix of the Erf-attenuated integrals for the CAM second pass (int2.F90:674-685)"""
@@ -359,3 +372,109 @@ def _mrsf_run_cam(self, drv: Int2Compute, alpha, beta, mu, alpha_coulomb, beta_c
 
 
 Int2MrsfData._run_cam = _mrsf_run_cam
+
+
+class Int2TdgrdData:
+    """int2_tdgrd_data_t (tdhf_lib.F90:33-36, update :228-295): the Z-vector / gradient response consumer with two spin
+    blocks.  d2: (2, nbf, nbf) [s][mu, nu]; results apb (2, nbf, nbf) symmetrised, amb (2, nbf, nbf) (block 2 stays zero)."""
+
+    def __init__(self, d2, int_apb=True, int_amb=False, scale_exchange=1.0, scale_coulomb=1.0):
+        self.d2 = np.asarray(d2, dtype=np.float64)
+        assert self.d2.shape[0] == 2
+        self.int_apb, self.int_amb = int_apb, int_amb
+        self.scale_exchange, self.scale_coulomb = scale_exchange, scale_coulomb
+        self.apb = self.amb = None
+        self.skipped = 0
+
+    def _run(self, drv: Int2Compute):
+        dF = np.ascontiguousarray(np.transpose(self.d2, (0, 2, 1)))  # Fortran (mu, nu, s)
+        apb, amb = np.zeros_like(dF), np.zeros_like(dF)
+        flags = (OQPB_TD_APB if self.int_apb else 0) | (OQPB_TD_AMB if self.int_amb else 0)
+        ns = C.c_longlong(0)
+        drv._check(lib().oqpb_jk_tdgrd(drv._h, _dp(dF), C.c_int(flags), C.c_double(self.scale_exchange),
+                                       C.c_double(self.scale_coulomb), _dp(apb), _dp(amb), C.byref(ns)), "oqpb_jk_tdgrd")
+        self.apb = np.transpose(apb, (0, 2, 1)).copy()
+        self.amb = np.transpose(amb, (0, 2, 1)).copy()
+        self.skipped = int(ns.value)
+
+
+class Int2RpagrdData:
+    """int2_rpagrd_data_t (tdhf_lib.F90:42-57, 1068-1320): xpy, xmy, t: (n, nspin, nbf, nbf) [q][s][mu, nu] or None;
+    results hpp = H+[X+Y], hpt = H+[T] (symmetrised), hmm = H-[X-Y] with the shapes of xpy, t, xmy.
+    X+Y and T must be symmetric matrices (as at every call site of the reference)."""
+
+    def __init__(self, xpy=None, xmy=None, t=None, nspin=1, scale_exchange=1.0, scale_coulomb=1.0):
+        self.nspin = nspin
+        self.xpy, self.xmy, self.t = xpy, xmy, t
+        self.scale_exchange, self.scale_coulomb = scale_exchange, scale_coulomb
+        self.hpp = self.hpt = self.hmm = None
+        self.skipped = 0
+
+    def _run(self, drv: Int2Compute):
+        nbf, nspin = drv.basis.nbf, self.nspin
+
+        def prep(a):
+            if a is None:
+                return np.zeros((0, nspin, nbf, nbf)), 0
+            a = np.asarray(a, dtype=np.float64)
+            assert a.shape[1:] == (nspin, nbf, nbf)
+            return np.ascontiguousarray(np.transpose(a, (0, 1, 3, 2))), a.shape[0]
+
+        X, npp = prep(self.xpy)
+        M, nm = prep(self.xmy)
+        T, nt = prep(self.t)
+        hpp, hpt, hmm = np.zeros_like(X), np.zeros_like(T), np.zeros_like(M)
+        ns = C.c_longlong(0)
+        drv._check(lib().oqpb_jk_rpagrd(drv._h, C.c_int(nspin), C.c_int(npp), C.c_int(nm), C.c_int(nt),
+                                        _dp(X) if npp else None, _dp(M) if nm else None, _dp(T) if nt else None,
+                                        C.c_double(self.scale_exchange), C.c_double(self.scale_coulomb),
+                                        _dp(hpp) if npp else None, _dp(hpt) if nt else None, _dp(hmm) if nm else None,
+                                        C.byref(ns)), "oqpb_jk_rpagrd")
+        tr = lambda a: np.transpose(a, (0, 1, 3, 2)).copy()
+        self.hpp, self.hpt, self.hmm = tr(hpp), tr(hpt), tr(hmm)
+        self.skipped = int(ns.value)
+
+
+class Int2UmrsfData:
+    """int2_umrsf_data_t (tdhf_mrsf_lib.F90:28-32, update :337-426).  d3: (nvec, 11, nbf, nbf); f3 likewise."""
+
+    def __init__(self, d3, scale_exchange=1.0, scale_coulomb=1.0):
+        self.d3 = np.asarray(d3, dtype=np.float64)
+        assert self.d3.shape[1] == 11
+        self.scale_exchange, self.scale_coulomb = scale_exchange, scale_coulomb
+        self.f3 = None
+        self.skipped = 0
+
+    def _run(self, drv: Int2Compute):
+        nv = self.d3.shape[0]
+        dF = np.ascontiguousarray(np.transpose(self.d3, (3, 2, 1, 0)))
+        f3 = np.zeros_like(dF)
+        ns = C.c_longlong(0)
+        drv._check(lib().oqpb_jk_umrsf(drv._h, _dp(dF), C.c_int(nv), C.c_double(self.scale_exchange),
+                                       C.c_double(self.scale_coulomb), _dp(f3), C.byref(ns)), "oqpb_jk_umrsf")
+        self.f3 = np.transpose(f3, (3, 2, 1, 0)).copy()
+        self.skipped = int(ns.value)
+
+    def _run_cam(self, drv: Int2Compute, alpha, beta, mu, alpha_coulomb, beta_coulomb):
+        nv = self.d3.shape[0]
+        dF = np.ascontiguousarray(np.transpose(self.d3, (3, 2, 1, 0)))
+        f3 = np.zeros_like(dF)
+        ns = C.c_longlong(0)
+        drv._check(lib().oqpb_jk_umrsf_cam(drv._h, _dp(dF), C.c_int(nv), C.c_double(alpha), C.c_double(beta), C.c_double(mu),
+                                           C.c_double(alpha_coulomb), _dp(f3), C.byref(ns)), "oqpb_jk_umrsf_cam")
+        self.f3 = np.transpose(f3, (3, 2, 1, 0)).copy()
+        self.skipped = int(ns.value)
+
+
+def jk(drv: Int2Compute, P, want_j=None, want_k=None):
+    """oqpb_jk: generic J/K of n general matrices P (n, nbf, nbf) [m][mu, nu]:
+    J_m(a,b) = sum_cd (ab|cd) P_m(c,d), K_m(a,c) = sum_bd (ab|cd) P_m(b,d).  Returns (J, K, nskipped)."""
+    P = np.asarray(P, dtype=np.float64)
+    n, nbf, _ = P.shape
+    wj = np.ones(n, dtype=np.int32) if want_j is None else np.asarray(want_j, dtype=np.int32)
+    wk = np.ones(n, dtype=np.int32) if want_k is None else np.asarray(want_k, dtype=np.int32)
+    PF = np.ascontiguousarray(np.transpose(P, (0, 2, 1)))
+    J, K = np.zeros_like(PF), np.zeros_like(PF)
+    ns = C.c_longlong(0)
+    drv._check(lib().oqpb_jk(drv._h, C.c_int(n), _dp(PF), _ip(wj), _ip(wk), _dp(J), _dp(K), C.byref(ns)), "oqpb_jk")
+    return np.transpose(J, (0, 2, 1)).copy(), np.transpose(K, (0, 2, 1)).copy(), int(ns.value)

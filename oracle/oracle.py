@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-RHF, UROHF, TD, MRSF = 0, 1, 2, 3
+RHF, UROHF, TD, MRSF, TDGRD, RPAGRD, UMRSF = 0, 1, 2, 3, 5, 6, 7
 
 
 def build(force: bool = False) -> str:
@@ -170,6 +170,54 @@ class Oracle:
                        stride, offset)
         return np.transpose(f3, (3, 2, 1, 0)).copy(), st
 
+    def tdgrd(self, d2, scale_exchange=1.0, scale_coulomb=1.0, int_apb=True, int_amb=False, nthreads=0):
+        """int2_tdgrd_data_t (tdhf_lib.F90:33-36, 228-295): d2 numpy (2, nbf, nbf) = two spin blocks P_s[mu, nu];
+        returns apb (2, nbf, nbf) symmetrised as parallel_stop does, amb (2, nbf, nbf) (second block stays zero)."""
+        nbf = self.basis.nbf
+        d2 = np.asarray(d2, dtype=np.float64)
+        assert d2.shape == (2, nbf, nbf)
+        dF = np.ascontiguousarray(np.transpose(d2, (0, 2, 1)))
+        apb = np.zeros_like(dF)
+        amb = np.zeros_like(dF)
+        flags = (1 if int_apb else 0) | (2 if int_amb else 0)
+        st = self._run(TDGRD, dF, 2, 0, scale_exchange, scale_coulomb, flags, apb, amb, nthreads, 0, -1, 1, 0)
+        lib().orc_td_post(C.c_int(nbf), C.c_int(2), _p(apb))
+        return np.transpose(apb, (0, 2, 1)).copy(), np.transpose(amb, (0, 2, 1)).copy(), st
+
+    def rpagrd(self, xpy=None, xmy=None, t=None, nspin=1, scale_exchange=1.0, scale_coulomb=1.0, nthreads=0):
+        """int2_rpagrd_data_t (tdhf_lib.F90:42-57, 1068-1320): inputs numpy (n, nspin, nbf, nbf) [q, s, mu, nu] or None;
+        returns hpp, hpt (symmetrised), hmm with the shapes of xpy, t, xmy."""
+        nbf = self.basis.nbf
+
+        def prep(a):
+            if a is None:
+                return np.zeros((0, nspin, nbf, nbf)), 0
+            a = np.asarray(a, dtype=np.float64)
+            assert a.shape[1:] == (nspin, nbf, nbf)
+            return np.ascontiguousarray(np.transpose(a, (0, 1, 3, 2))), a.shape[0]  # Fortran (mu, nu, s, q)
+
+        X, npp = prep(xpy)
+        M, nm = prep(xmy)
+        T, nt = prep(t)
+        hpp, hpt, hmm = np.zeros_like(X), np.zeros_like(T), np.zeros_like(M)
+        st = np.zeros(3, dtype=np.int64)
+        lib().orc_run_rpagrd(self.h, C.c_int(nspin), C.c_int(npp), C.c_int(nm), C.c_int(nt), _p(X) if npp else None,
+                             _p(M) if nm else None, _p(T) if nt else None, C.c_double(scale_exchange), C.c_double(scale_coulomb),
+                             _p(hpp) if npp else None, _p(hpt) if nt else None, _p(hmm) if nm else None, C.c_int(nthreads),
+                             _p(st, C.c_long))
+        tr = lambda a: np.transpose(a, (0, 1, 3, 2)).copy()
+        return tr(hpp), tr(hpt), tr(hmm), {"nschwz": int(st[0]), "nquartets": int(st[1]), "nints": int(st[2])}
+
+    def umrsf(self, d3, scale_exchange=1.0, scale_coulomb=1.0, nthreads=0, cur_pass=1):
+        """int2_umrsf_data_t (tdhf_mrsf_lib.F90:28-32, 337-426): d3 numpy (nvec, 11, nbf, nbf); returns f3 likewise."""
+        d3 = np.asarray(d3, dtype=np.float64)
+        nv, nc, nbf, _ = d3.shape
+        assert nc == 11
+        dF = np.ascontiguousarray(np.transpose(d3, (3, 2, 1, 0)))
+        f3 = np.zeros_like(dF)
+        st = self._run(UMRSF, dF, nv, nc, scale_exchange, scale_coulomb, 16 if cur_pass == 2 else 0, f3, None, nthreads, 0, -1, 1, 0)
+        return np.transpose(f3, (3, 2, 1, 0)).copy(), st
+
     def mrsf_cam(self, d3, alpha, beta, mu, alpha_coulomb=1.0, beta_coulomb=0.0, nthreads=0):
         """int2_run_cam with the MRSF consumer: pass 1 regular (all components), pass 2 attenuated integrals, exchange of
         component 7 only (tdhf_mrsf_lib.F90:312-326)."""
@@ -203,6 +251,25 @@ class Oracle:
             out = np.zeros((n, 4), dtype=np.int32)
             lib().orc_quartet_list(self.h, _p(d), C.c_int(d.shape[0]), _p(out, C.c_int), C.c_long(n), C.byref(ns))
         return out, int(n), int(ns.value)
+
+    def pair_order(self):
+        """cost-sorted bra shell-pair list (int2.F90:864-921) as (npairs, 2) [i, j], i >= j, 0-based"""
+        L = lib()
+        L.orc_pair_order.restype = C.c_long
+        n = L.orc_pair_order(self.h, None, None)
+        pi = np.zeros(n, dtype=np.int32)
+        pj = np.zeros(n, dtype=np.int32)
+        L.orc_pair_order(self.h, _p(pi, C.c_int), _p(pj, C.c_int))
+        return np.stack([pi, pj], axis=1)
+
+    def sample_mask(self, stride, offset):
+        """byte mask over canonical pair ids i(i+1)/2+j of the bra pairs a (stride, offset) run visits"""
+        po = self.pair_order()
+        sel = ((np.arange(len(po)) + 1) % stride) == offset if stride > 1 else np.ones(len(po), bool)
+        mask = np.zeros(len(po), dtype=np.uint8)
+        ij = po[sel].astype(np.int64)
+        mask[ij[:, 0] * (ij[:, 0] + 1) // 2 + ij[:, 1]] = 1
+        return mask
 
     def shlden(self, kind, d, nfocks, ncomp=0):
         ns = self.basis.nshell

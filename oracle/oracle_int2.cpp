@@ -590,7 +590,7 @@ void ints_exchange(Oracle &o, double mu = 0.0) {
 }
 
 // Consumers -------------------------------------------------------------------------------------
-enum Kind { RHF = 0, UROHF = 1, TD = 2, MRSF = 3, COLLECT = 4 };
+enum Kind { RHF = 0, UROHF = 1, TD = 2, MRSF = 3, COLLECT = 4, TDGRD = 5, RPAGRD = 6, UMRSF = 7 };
 
 struct Consumer {
   int kind = RHF, nbf = 0, nfocks = 1;
@@ -605,6 +605,11 @@ struct Consumer {
   std::vector<double> ds;
   std::vector<double> dsh;
   double max_den = 0;
+  // RPAGRD (tdhf_lib.F90:42-57): xpy/xmy/t (nbf,nbf,nspin,n*) column-major; outputs hpp | hpt | hmm packed behind each
+  // other in the one accumulator f (offsets rp_off[0..2])
+  const double *xpy = nullptr, *xmy = nullptr, *tt = nullptr;
+  int nspin = 1, np = 0, nm = 0, nt = 0;
+  size_t rp_off[3] = {0, 0, 0};
 };
 
 struct Buf {  // int2_storage_t, int2.F90:60-80
@@ -720,6 +725,114 @@ void update(const Consumer &c, Buf &buf, double *f, double *f2, std::vector<int1
           F3(v, cc, j, l) -= xval * D3(v, cc, i, k); F3(v, cc, l, j) -= xval * D3(v, cc, k, i);
         }
     }
+  } else if (c.kind == TDGRD) {
+    // int2_tdgrd_data_t_update, tdhf_lib.F90:228-295: two spin blocks d2(:,:,1:2); A+B for both, A-B for the first
+    double xval1 = 1 * c.se, xval2 = 2 * c.sc;
+    const double *P1 = c.d, *P2 = c.d + n2;
+    double *apb1 = f, *apb2 = f + n2, *amb1 = f2;
+    auto D1 = [&](int a, int b) { return P1[(a - 1) + (size_t)nbf * (b - 1)]; };
+    auto D2 = [&](int a, int b) { return P2[(a - 1) + (size_t)nbf * (b - 1)]; };
+    auto A = [&](double *m, int a, int b) -> double & { return m[(a - 1) + (size_t)nbf * (b - 1)]; };
+    for (int n = 0; n < buf.ncur; n++) {
+      int i = buf.ids[4 * n], j = buf.ids[4 * n + 1], k = buf.ids[4 * n + 2], l = buf.ids[4 * n + 3];
+      double val = buf.ints[n], val1 = val * xval1, val2 = val * xval2;
+      if (c.int_apb) {
+        double ckl = val2 * (D1(k, l) + D1(l, k) + D2(k, l) + D2(l, k)), cij = val2 * (D1(i, j) + D1(j, i) + D2(i, j) + D2(j, i));
+        A(apb1, i, j) += ckl; A(apb1, k, l) += cij;
+        A(apb2, i, j) += ckl; A(apb2, k, l) += cij;
+        A(apb1, i, k) -= val1 * (D1(j, l) + D1(l, j)); A(apb1, i, l) -= val1 * (D1(j, k) + D1(k, j));
+        A(apb1, j, k) -= val1 * (D1(i, l) + D1(l, i)); A(apb1, j, l) -= val1 * (D1(i, k) + D1(k, i));
+        A(apb2, i, k) -= val1 * (D2(j, l) + D2(l, j)); A(apb2, i, l) -= val1 * (D2(j, k) + D2(k, j));
+        A(apb2, j, k) -= val1 * (D2(i, l) + D2(l, i)); A(apb2, j, l) -= val1 * (D2(i, k) + D2(k, i));
+      }
+      if (c.int_amb) {
+        A(amb1, i, k) += val1 * (D1(l, j) - D1(j, l)); A(amb1, i, l) += val1 * (D1(k, j) - D1(j, k));
+        A(amb1, j, k) += val1 * (D1(l, i) - D1(i, l)); A(amb1, j, l) += val1 * (D1(k, i) - D1(i, k));
+        A(amb1, k, i) -= val1 * (D1(l, j) - D1(j, l)); A(amb1, l, i) -= val1 * (D1(k, j) - D1(j, k));
+        A(amb1, k, j) -= val1 * (D1(l, i) - D1(i, l)); A(amb1, l, j) -= val1 * (D1(k, i) - D1(i, k));
+      }
+    }
+  } else if (c.kind == RPAGRD) {
+    // int2_rpagrd_data_t_update / _hplus / _hminus, tdhf_lib.F90:1177-1320
+    const size_t slab = n2 * c.nspin;
+    auto hplus = [&](double *hp, const double *v) {
+      auto V = [&](int a, int b, int s) { return v[(a - 1) + (size_t)nbf * (b - 1) + n2 * s]; };
+      auto H = [&](int a, int b, int s) -> double & { return hp[(a - 1) + (size_t)nbf * (b - 1) + n2 * s]; };
+      if (c.nspin == 1) {
+        double xfact = 2 * c.se, cfact = 8 * c.sc;
+        for (int n = 0; n < buf.ncur; n++) {
+          int i = buf.ids[4 * n], j = buf.ids[4 * n + 1], k = buf.ids[4 * n + 2], l = buf.ids[4 * n + 3];
+          double val = buf.ints[n], xval = val * xfact, cval = val * cfact;
+          H(i, j, 0) += cval * V(l, k, 0); H(k, l, 0) += cval * V(j, i, 0);
+          H(i, k, 0) -= xval * V(l, j, 0); H(i, l, 0) -= xval * V(k, j, 0);
+          H(j, k, 0) -= xval * V(l, i, 0); H(j, l, 0) -= xval * V(k, i, 0);
+        }
+      } else {
+        double xfact = 1 * c.se, cfact = 2 * c.sc;
+        for (int n = 0; n < buf.ncur; n++) {
+          int i = buf.ids[4 * n], j = buf.ids[4 * n + 1], k = buf.ids[4 * n + 2], l = buf.ids[4 * n + 3];
+          double val = buf.ints[n], xval = val * xfact, cval = val * cfact;
+          double ckl = cval * (V(k, l, 0) + V(l, k, 0) + V(k, l, 1) + V(l, k, 1));
+          double cij = cval * (V(i, j, 0) + V(j, i, 0) + V(i, j, 1) + V(j, i, 1));
+          for (int sp = 0; sp < 2; sp++) {
+            H(i, j, sp) += ckl; H(k, l, sp) += cij;
+            H(i, k, sp) -= xval * (V(j, l, sp) + V(l, j, sp)); H(i, l, sp) -= xval * (V(j, k, sp) + V(k, j, sp));
+            H(j, k, sp) -= xval * (V(i, l, sp) + V(l, i, sp)); H(j, l, sp) -= xval * (V(i, k, sp) + V(k, i, sp));
+          }
+        }
+      }
+    };
+    auto hminus = [&](double *hm, const double *v) {  // first spin block only, as written (:1297-1318)
+      auto V = [&](int a, int b) { return v[(a - 1) + (size_t)nbf * (b - 1)]; };
+      auto H = [&](int a, int b) -> double & { return hm[(a - 1) + (size_t)nbf * (b - 1)]; };
+      double xfact = c.se;
+      for (int n = 0; n < buf.ncur; n++) {
+        int i = buf.ids[4 * n], j = buf.ids[4 * n + 1], k = buf.ids[4 * n + 2], l = buf.ids[4 * n + 3];
+        double xval = buf.ints[n] * xfact;
+        H(i, k) += xval * (V(l, j) - V(j, l)); H(i, l) += xval * (V(k, j) - V(j, k));
+        H(j, k) += xval * (V(l, i) - V(i, l)); H(j, l) += xval * (V(k, i) - V(i, k));
+        H(k, i) -= xval * (V(l, j) - V(j, l)); H(l, i) -= xval * (V(k, j) - V(j, k));
+        H(k, j) -= xval * (V(l, i) - V(i, l)); H(l, j) -= xval * (V(k, i) - V(i, k));
+      }
+    };
+    for (int q = 0; q < c.np; q++) hplus(f + c.rp_off[0] + q * slab, c.xpy + q * slab);
+    for (int q = 0; q < c.nt; q++) hplus(f + c.rp_off[1] + q * slab, c.tt + q * slab);
+    for (int q = 0; q < c.nm; q++) hminus(f + c.rp_off[2] + q * slab, c.xmy + q * slab);
+  } else if (c.kind == UMRSF) {
+    // int2_umrsf_data_t_update, tdhf_mrsf_lib.F90:337-426 (11 components; 1-8 Coulomb + exchange, 9-10 the mixed-spin
+    // exchange permutation, 11 plain exchange; pass 2 = component 11 only)
+    const int nf = c.nfocks, nc = c.ncomp;
+    auto D3 = [&](int v, int cc, int a, int b) { return c.d[v + (size_t)nf * (cc + (size_t)nc * ((a - 1) + (size_t)nbf * (b - 1)))]; };
+    auto F3 = [&](int v, int cc, int a, int b) -> double & { return f[v + (size_t)nf * (cc + (size_t)nc * ((a - 1) + (size_t)nbf * (b - 1)))]; };
+    for (int n = 0; n < buf.ncur; n++) {
+      int i = buf.ids[4 * n], j = buf.ids[4 * n + 1], k = buf.ids[4 * n + 2], l = buf.ids[4 * n + 3];
+      double val = buf.ints[n], xval = val * c.se, cval = val * c.sc;
+      for (int v = 0; v < nf; v++) {
+        if (c.cur_pass == 1) {
+          for (int cc = 0; cc < 8; cc++) {
+            F3(v, cc, i, j) += cval * D3(v, cc, k, l); F3(v, cc, k, l) += cval * D3(v, cc, i, j);
+            F3(v, cc, i, j) += cval * D3(v, cc, l, k); F3(v, cc, l, k) += cval * D3(v, cc, i, j);
+            F3(v, cc, j, i) += cval * D3(v, cc, k, l); F3(v, cc, k, l) += cval * D3(v, cc, j, i);
+            F3(v, cc, j, i) += cval * D3(v, cc, l, k); F3(v, cc, l, k) += cval * D3(v, cc, j, i);
+            F3(v, cc, i, k) -= xval * D3(v, cc, j, l); F3(v, cc, k, i) -= xval * D3(v, cc, l, j);
+            F3(v, cc, i, l) -= xval * D3(v, cc, j, k); F3(v, cc, l, i) -= xval * D3(v, cc, k, j);
+            F3(v, cc, j, k) -= xval * D3(v, cc, i, l); F3(v, cc, k, j) -= xval * D3(v, cc, l, i);
+            F3(v, cc, j, l) -= xval * D3(v, cc, i, k); F3(v, cc, l, j) -= xval * D3(v, cc, k, i);
+          }
+          for (int cc = 8; cc < 10; cc++) {
+            F3(v, cc, i, l) -= xval * D3(v, cc, k, j); F3(v, cc, l, i) -= xval * D3(v, cc, j, k);
+            F3(v, cc, k, j) -= xval * D3(v, cc, i, l); F3(v, cc, j, k) -= xval * D3(v, cc, l, i);
+            F3(v, cc, i, k) -= xval * D3(v, cc, l, j); F3(v, cc, k, i) -= xval * D3(v, cc, j, l);
+            F3(v, cc, l, j) -= xval * D3(v, cc, i, k); F3(v, cc, j, l) -= xval * D3(v, cc, k, i);
+          }
+        }
+        const int cc = 10;
+        F3(v, cc, i, k) -= xval * D3(v, cc, j, l); F3(v, cc, k, i) -= xval * D3(v, cc, l, j);
+        F3(v, cc, i, l) -= xval * D3(v, cc, j, k); F3(v, cc, l, i) -= xval * D3(v, cc, k, j);
+        F3(v, cc, j, k) -= xval * D3(v, cc, i, l); F3(v, cc, k, j) -= xval * D3(v, cc, l, i);
+        F3(v, cc, j, l) -= xval * D3(v, cc, i, k); F3(v, cc, l, j) -= xval * D3(v, cc, k, i);
+      }
+    }
   } else if (c.kind == COLLECT) {
     for (int n = 0; n < buf.ncur; n++) {
       for (int t = 0; t < 4; t++) collect_ids->push_back(buf.ids[4 * n + t]);
@@ -790,11 +903,20 @@ void init_screen(const Basis &b, Consumer &c) {
             int mj = (si == sj) ? i : maxj;
             for (int j = minj; j <= mj; j++) dmax = std::max(dmax, std::fabs(c.d[f * ntri + tri(i, j)]));
           }
-      } else if (c.kind == TD) {  // da(minj:maxj, mini:maxi, :)
+      } else if (c.kind == RPAGRD) {  // shlrpagrd over xpy, xmy (guarded by np, as written) and t: tdhf_lib.F90:1161-1173
+        auto blockmax = [&](const double *v, int cnt) {
+          for (size_t q = 0; q < (size_t)cnt * c.nspin; q++)
+            for (int i = mini; i <= maxi; i++)
+              for (int j = minj; j <= maxj; j++) dmax = std::max(dmax, std::fabs(v[q * n2 + j + (size_t)nbf * i]));
+        };
+        if (c.np > 0) blockmax(c.xpy, c.np);
+        if (c.np > 0 && c.xmy) blockmax(c.xmy, c.nm);
+        if (c.nt > 0) blockmax(c.tt, c.nt);
+      } else if (c.kind == TD || c.kind == TDGRD) {  // da(minj:maxj, mini:maxi, :)
         for (int v = 0; v < c.nfocks; v++)
           for (int i = mini; i <= maxi; i++)
             for (int j = minj; j <= maxj; j++) dmax = std::max(dmax, std::fabs(c.d[v * n2 + j + (size_t)nbf * i]));
-      } else if (c.kind == MRSF) {  // da(:, minj:maxj, mini:maxi) with da = d3 viewed (nvec*ncomp, nbf, nbf)
+      } else if (c.kind == MRSF || c.kind == UMRSF) {  // da(:, minj:maxj, mini:maxi) with da = d3 viewed (nvec*ncomp, nbf, nbf)
         int nm = c.nfocks * c.ncomp;
         for (int i = mini; i <= maxi; i++)
           for (int j = minj; j <= maxj; j++)
@@ -1109,7 +1231,8 @@ void orc_run(void *h, int kind, const double *d, int nfocks, int ncomp, double s
   c.cur_pass = (flags >> 4) & 1 ? 2 : 1;
   size_t nbf = c.nbf, ntri = nbf * (nbf + 1) / 2, fs = 0, f2s = 0;
   if (kind == RHF || kind == UROHF) fs = ntri * nfocks;
-  if (kind == TD) { fs = nbf * nbf * nfocks; f2s = fs; }
+  if (kind == TD || kind == TDGRD) { fs = nbf * nbf * nfocks; f2s = fs; }
+  if (kind == UMRSF) fs = nbf * nbf * nfocks * ncomp;
   if (kind == MRSF) {
     fs = nbf * nbf * nfocks * ncomp;
     c.ds.assign(nbf * nbf * nfocks * 4, 0.0);  // tdhf_mrsf_lib.F90:86-92
@@ -1124,6 +1247,34 @@ void orc_run(void *h, int kind, const double *d, int nfocks, int ncomp, double s
   if (f2s) std::fill(f2, f2 + f2s, 0.0);
   RunStats st;
   twoei(*o, c, f, f2, fs, f2s, nthreads, pair_lo, pair_hi, stride, offset, st, nullptr, nullptr, nullptr);
+  if (stats) { stats[0] = st.nschwz; stats[1] = st.nshq; stats[2] = st.nint; }
+}
+
+// int2_rpagrd_data_t (tdhf_lib.F90:42-57, 1068-1320): H+[X+Y] -> hpp, H+[T] -> hpt (both symmetrised at stop, :1138-1141),
+// H-[X-Y] -> hmm; arrays (nbf, nbf, nspin, n) column-major
+void orc_run_rpagrd(void *h, int nspin, int np, int nm, int nt, const double *xpy, const double *xmy, const double *t,
+                    double se, double sc, double *hpp, double *hpt, double *hmm, int nthreads, long *stats) {
+  Oracle *o = (Oracle *)h;
+  Consumer c;
+  c.kind = RPAGRD; c.nbf = o->b.nbf; c.se = se; c.sc = sc;
+  c.nspin = nspin; c.np = np; c.nm = nm; c.nt = nt; c.xpy = xpy; c.xmy = xmy; c.tt = t;
+  const size_t n2 = (size_t)c.nbf * c.nbf, slab = n2 * nspin;
+  c.rp_off[0] = 0; c.rp_off[1] = slab * np; c.rp_off[2] = slab * (np + nt);
+  std::vector<double> f(slab * (np + nt + nm), 0.0);
+  RunStats st;
+  twoei(*o, c, f.data(), nullptr, f.size(), 0, nthreads, 0, -1, 1, 0, st, nullptr, nullptr, nullptr);
+  for (size_t q = 0; q < slab * np; q++) hpp[q] = f[q];
+  for (size_t q = 0; q < slab * nt; q++) hpt[q] = f[c.rp_off[1] + q];
+  for (size_t q = 0; q < slab * nm; q++) hmm[q] = f[c.rp_off[2] + q];
+  auto symm = [&](double *a, size_t cnt) {  // symmetrize_matrices
+    for (size_t m = 0; m < cnt; m++) {
+      double *x = a + m * n2;
+      for (int i = 0; i < c.nbf; i++)
+        for (int j = 0; j <= i; j++) { double s2 = x[i + (size_t)c.nbf * j] + x[j + (size_t)c.nbf * i]; x[i + (size_t)c.nbf * j] = x[j + (size_t)c.nbf * i] = s2; }
+    }
+  };
+  symm(hpp, (size_t)np * nspin);
+  symm(hpt, (size_t)nt * nspin);
   if (stats) { stats[0] = st.nschwz; stats[1] = st.nshq; stats[2] = st.nint; }
 }
 
@@ -1214,6 +1365,15 @@ void orc_dense_eri(void *h, double *eri) {
 
 void orc_int1e(void *h, int natom, const double *Z, const double *xyz, double *S, double *T, double *V) {
   int1e(((Oracle *)h)->b, natom, Z, xyz, S, T, V);
+}
+
+// cost-sorted bra shell-pair order of int2_build_shell_pair_map (int2.F90:864-921): pi[p] >= pj[p], 0-based
+long orc_pair_order(void *h, int *pi_out, int *pj_out) {
+  Oracle *o = (Oracle *)h;
+  std::vector<int> pi, pj;
+  build_pair_map(*o, pi, pj);
+  if (pi_out) for (size_t k = 0; k < pi.size(); k++) { pi_out[k] = pi[k]; pj_out[k] = pj[k]; }
+  return (long)pi.size();
 }
 
 int orc_max_threads() {

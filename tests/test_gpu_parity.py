@@ -423,3 +423,71 @@ def test_edge_cases(oracle_mod, drv):
     cm = drv.run(Int2MrsfData(d3, scale_exchange=0.5, scale_coulomb=1.0))
     fm, stm = o.mrsf(d3, 0.5, 1.0)
     assert np.abs(cm.f3 - fm).max() < FOCK_TOL and cm.skipped == stm["nschwz"]
+
+
+def test_generic_jk_against_dense_eri(oracle_mod, drv):
+    """oqpb_jk: J[P](a,b) = sum (ab|cd) P(c,d), K[P](a,c) = sum (ab|cd) P(b,d) for general (non-symmetric) P, against the
+    oracle's dense ERI tensor; J-only / K-only selection leaves the other slabs untouched."""
+    from openqp_b200.int2 import jk
+    bs, o = _pair(oracle_mod, drv, B.water(), "cc-pvdz", cutoff=1e-14)
+    eri = o.dense_eri()
+    rng = np.random.default_rng(17)
+    P = rng.normal(size=(3, bs.nbf, bs.nbf)) * 0.1
+    J, K, _ = jk(drv, P, want_j=[1, 0, 1], want_k=[1, 1, 0])
+    for m in range(3):
+        Jr = np.einsum("abcd,cd->ab", eri, P[m])
+        Kr = np.einsum("abcd,bd->ac", eri, P[m])
+        if m != 1:
+            assert np.abs(J[m] - Jr).max() < 1e-11
+        else:
+            assert np.abs(J[m]).max() == 0.0
+        if m != 2:
+            assert np.abs(K[m] - Kr).max() < 1e-11
+        else:
+            assert np.abs(K[m]).max() == 0.0
+
+
+def test_gradient_response_consumers(oracle_mod, drv):
+    """int2_tdgrd_data_t (tdhf_lib.F90:228-295), int2_rpagrd_data_t (:1068-1320, nspin 1 and 2) and int2_umrsf_data_t
+    (tdhf_mrsf_lib.F90:337-426) through the generic J/K engine, against the oracle's line-by-line restatements
+    (quartet lists identical: same Schwarz matrix, same shell densities)."""
+    from openqp_b200.int2 import Int2RpagrdData, Int2TdgrdData, Int2UmrsfData
+    bs, o = _pair(oracle_mod, drv, B.water_dimer(), "cc-pvdz", cutoff=1e-9, upload_q=True)
+    rng = np.random.default_rng(23)
+    n = bs.nbf
+    se, sc = 0.6, 0.8
+    d2 = rng.normal(size=(2, n, n)) * 0.1
+    c = drv.run(Int2TdgrdData(d2, int_apb=True, int_amb=True, scale_exchange=se, scale_coulomb=sc))
+    apb, amb, st = o.tdgrd(d2, se, sc, True, True)
+    assert np.abs(c.apb - apb).max() < 1e-10 and np.abs(c.amb - amb).max() < 1e-10
+    assert c.skipped == st["nschwz"] and st["nschwz"] > 0
+    c = drv.run(Int2TdgrdData(d2, int_apb=True, int_amb=False, scale_exchange=se, scale_coulomb=sc))
+    apb, amb, st = o.tdgrd(d2, se, sc, True, False)
+    assert np.abs(c.apb - apb).max() < 1e-10 and np.abs(c.amb).max() == 0.0
+    sym = lambda a: a + np.swapaxes(a, -1, -2)
+    xpy, t = sym(rng.normal(size=(2, 1, n, n)) * 0.1), sym(rng.normal(size=(1, 1, n, n)) * 0.1)
+    xmy = rng.normal(size=(2, 1, n, n)) * 0.1
+    c = drv.run(Int2RpagrdData(xpy, xmy, t, 1, se, sc))
+    hpp, hpt, hmm, st = o.rpagrd(xpy, xmy, t, 1, se, sc)
+    assert np.abs(c.hpp - hpp).max() < 1e-10 and np.abs(c.hpt - hpt).max() < 1e-10 and np.abs(c.hmm - hmm).max() < 1e-10
+    assert c.skipped == st["nschwz"]
+    c = drv.run(Int2RpagrdData(None, None, t, 1, se, sc))  # the H+[T+Z] call of tdhf_z_vector.F90:341
+    _, hpt, _, st = o.rpagrd(None, None, t, 1, se, sc)
+    assert np.abs(c.hpt - hpt).max() < 1e-10 and c.skipped == st["nschwz"]
+    xpy2, xmy2 = rng.normal(size=(1, 2, n, n)) * 0.1, rng.normal(size=(1, 2, n, n)) * 0.1
+    c = drv.run(Int2RpagrdData(xpy2, xmy2, None, 2, se, sc))
+    hpp, _, hmm, st = o.rpagrd(xpy2, xmy2, None, 2, se, sc)
+    assert np.abs(c.hpp - hpp).max() < 1e-10 and np.abs(c.hmm - hmm).max() < 1e-10 and c.skipped == st["nschwz"]
+    d3 = rng.normal(size=(2, 11, n, n)) * 0.1
+    c = drv.run(Int2UmrsfData(d3, se, sc))
+    f3, st = o.umrsf(d3, se, sc)
+    assert np.abs(c.f3 - f3).max() < 1e-10 and c.skipped == st["nschwz"]
+    # range-separated variant: pass 2 = attenuated exchange of component 11 only
+    mu, alpha, beta = 0.33, 0.19, 0.46
+    drv.set_screening_cam(mu, o.schwarz_attenuated(mu))
+    c = drv.run(Int2UmrsfData(d3), cam=True, alpha=alpha, beta=beta, mu=mu)
+    f1, _ = o.umrsf(d3, alpha, 1.0)
+    o.set_attenuation(mu)
+    f2, _ = o.umrsf(d3, beta, 0.0, cur_pass=2)
+    o.set_attenuation(0.0)
+    assert np.abs(c.f3 - (f1 + f2)).max() < 1e-10 and np.abs(f2[:, 10]).max() > 1e-5 and np.abs(f2[:, :10]).max() == 0.0

@@ -227,3 +227,44 @@ def test_oracle_strided_partitions_sum_to_full(oracle_mod):
     p3 = [o.mrsf(d3, 0.5, 1.0, stride=2, offset=r) for r in range(2)]
     assert np.abs(p3[0][0] + p3[1][0] - f3).max() < 1e-12
     assert p3[0][1]["nquartets"] + p3[1][1]["nquartets"] == st3["nquartets"]
+
+
+def test_oracle_gradient_response_consumers_vs_dense_eri(oracle_mod):
+    """The restatements of int2_tdgrd_data_t / int2_rpagrd_data_t / int2_umrsf_data_t (tdhf_lib.F90:228-295, 1068-1320;
+    tdhf_mrsf_lib.F90:337-426) against plain J/K algebra on the dense ERI tensor."""
+    from openqp_b200 import basis as B
+    bs = B.BasisSet(B.water(), "6-31g(d)")
+    o = oracle_mod.Oracle(bs, 1e-14)
+    o.set_screening()
+    eri = o.dense_eri()
+    n = bs.nbf
+    J = lambda P: np.einsum("abcd,cd->ab", eri, P)
+    K = lambda P: np.einsum("abcd,bd->ac", eri, P)
+    rng = np.random.default_rng(0)
+    se, sc = 0.7, 0.9
+    d2 = rng.normal(size=(2, n, n)) * 0.1
+    apb, amb, _ = o.tdgrd(d2, se, sc, True, True)
+    for s_ in range(2):
+        assert np.abs(apb[s_] - (2 * sc * J(d2[0] + d2[1]) - se * K(d2[s_] + d2[s_].T))).max() < 1e-13
+    assert np.abs(amb[0] - se * K(d2[0].T - d2[0])).max() < 1e-13 and np.abs(amb[1]).max() == 0.0
+    sym = lambda a: a + np.swapaxes(a, -1, -2)
+    xpy, t, xmy = sym(rng.normal(size=(2, 1, n, n)) * 0.1), sym(rng.normal(size=(1, 1, n, n)) * 0.1), rng.normal(size=(2, 1, n, n)) * 0.1
+    hpp, hpt, hmm, _ = o.rpagrd(xpy, xmy, t, 1, se, sc)
+    for q in range(2):
+        assert np.abs(hpp[q, 0] - (4 * sc * J(xpy[q, 0]) - 2 * se * K(xpy[q, 0]))).max() < 1e-13
+        assert np.abs(hmm[q, 0] - se * K(xmy[q, 0].T - xmy[q, 0])).max() < 1e-13
+    assert np.abs(hpt[0, 0] - (4 * sc * J(t[0, 0]) - 2 * se * K(t[0, 0]))).max() < 1e-13
+    xpy2, xmy2 = rng.normal(size=(1, 2, n, n)) * 0.1, rng.normal(size=(1, 2, n, n)) * 0.1
+    hpp, _, hmm, _ = o.rpagrd(xpy2, xmy2, None, 2, se, sc)
+    for s_ in range(2):
+        assert np.abs(hpp[0, s_] - (2 * sc * J(xpy2[0, 0] + xpy2[0, 1]) - se * K(xpy2[0, s_] + xpy2[0, s_].T))).max() < 1e-13
+    assert np.abs(hmm[0, 0] - se * K(xmy2[0, 0].T - xmy2[0, 0])).max() < 1e-13 and np.abs(hmm[0, 1]).max() == 0.0
+    d3 = rng.normal(size=(2, 11, n, n)) * 0.1
+    for cur_pass in (1, 2):
+        f3, _ = o.umrsf(d3, se, sc, cur_pass=cur_pass)
+        for v in range(2):
+            for c in range(11):
+                ref = (sc * J(d3[v, c]) if c < 8 else 0.0) - se * K(d3[v, c].T if c in (8, 9) else d3[v, c])
+                if cur_pass == 2 and c < 10:
+                    ref = 0.0 * ref
+                assert np.abs(f3[v, c] - ref).max() < 1e-13
