@@ -53,3 +53,34 @@ def test_sass_is_sm100a(libpath):
     import subprocess
     out = subprocess.run(["cuobjdump", "--list-elf", libpath], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_header_is_plain_c99_and_a_c_host_links(libpath, tmp_path):
+    """include/oqp_b200.h is consumed by a C translation unit (not only through ctypes): strict C99 syntax check of the
+    header and of tests/c/routec_driver.c, then a real link of the C host program against the library."""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    src = os.path.join(ROOT, "tests", "c", "routec_driver.c")
+    tu = tmp_path / "hdr_only.c"
+    tu.write_text('#include "oqp_b200.h"\nint main(void) { return OQPB_OK; }\n')
+    for f in (str(tu), src):
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, f],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    exe = tmp_path / "routec_driver"
+    r = subprocess.run(["gcc", "-std=c99", "-I", inc, src, "-o", str(exe), "-L", os.path.dirname(libpath), "-lopenqp_b200",
+                        "-Wl,-rpath," + os.path.dirname(libpath)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_reference_arm_uses_all_host_threads_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must still use every host core."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1", "--steps", "1",
+                          "--warmup", "0", "--cpu-seconds", "0.5"], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-500:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))

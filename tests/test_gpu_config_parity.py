@@ -5,7 +5,7 @@
   w32 (H2O)32/cc-pVTZ     strided sample of the reference's cost-sorted bra-pair list: the oracle visits every
   c4  (H2O)64/cc-pVTZ     n-th bra pair (int2.F90:759-761 semantics) and the GPU is restricted to the SAME bra pairs
                           through oqpb_set_bra_mask; partial Fock matrices and quartet counts must agree
-  ERI blocks of >= 200 w32 quartets covering all 55 angular-momentum classes with 3-4 distinct centres
+  ERI blocks of >= 200 benzene/cc-pVTZ quartets covering all 55 angular-momentum classes with 3-4 distinct centres
   converged RHF energies through the GPU against the oracle SCF (5d/7f bases)
 
 Tolerances as everywhere: quartet counts exact, Fock / f3 elements 1e-10 Eh absolute, SCF energies 1e-10 vs the oracle.
@@ -126,9 +126,10 @@ def test_sampled_fock_vs_oracle(oracle_mod, drv, cfg, stride):
 
 
 def test_eri_blocks_all_classes_many_centres(oracle_mod, drv):
-    """shellquartet on (H2O)8/cc-pVTZ: >= 200 quartets, all 55 classes, each on 3 or 4 distinct centres (f shells on
-    different oxygens, which the water / water-dimer tests cannot offer)."""
-    mol, bs = B.build("w8")
+    """shellquartet on benzene/cc-pVTZ: >= 200 quartets, all 55 classes, each on 3 or 4 distinct centres (f shells on
+    different, bonded carbons -- in a water cluster f shells of different oxygens do not overlap: Q ~ 1e-11)."""
+    mol = B.benzene()
+    bs = B.BasisSet(mol, "cc-pvtz")
     o = oracle_mod.Oracle(bs)
     q = o.set_screening()
     drv.init(bs)

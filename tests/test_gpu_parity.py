@@ -491,3 +491,40 @@ def test_gradient_response_consumers(oracle_mod, drv):
     f2, _ = o.umrsf(d3, beta, 0.0, cur_pass=2)
     o.set_attenuation(0.0)
     assert np.abs(c.f3 - (f1 + f2)).max() < 1e-10 and np.abs(f2[:, 10]).max() > 1e-5 and np.abs(f2[:, :10]).max() == 0.0
+
+
+def test_c_host_program(oracle_mod, tmp_path):
+    """A C99 program (tests/c/routec_driver.c) drives the boundary: routec_fock_jk by reference on a registered context,
+    oqpb_fock, and -- with two GPUs visible -- the multi-device context.  Its Fock matrices are compared with the oracle."""
+    import os
+    import struct
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "openqp_b200")
+    exe = tmp_path / "routec_driver"
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "c", "routec_driver.c"),
+                        "-o", str(exe), "-L", libdir, "-lopenqp_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    bs = B.BasisSet(B.water_dimer(), "cc-pvdz")
+    d = np.ascontiguousarray(pack(decaying_density(bs)))
+    dump = tmp_path / "dump.bin"
+    with open(dump, "wb") as f:
+        f.write(struct.pack("4i", bs.nshell, bs.nprim, bs.nbf, 1 if bs.spherical else 0))
+        for a in (bs.am, bs.harmonic, bs.ncontr, bs.g_offset, bs.ao_offset, bs.naos):
+            f.write(np.ascontiguousarray(a, dtype=np.int32).tobytes())
+        for a in (bs.ex, bs.cc, bs.centers, d):
+            f.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    out = tmp_path / "out.bin"
+    r = subprocess.run([str(exe), str(dump), str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = open(out, "rb").read()
+    nskipped, ndev = struct.unpack("qi", raw[:12])
+    f3 = np.frombuffer(raw[12:], dtype=np.float64).reshape(3, bs.ntri)
+    o = oracle_mod.Oracle(bs)
+    o.set_screening()
+    fo, st = o.fock(d)
+    assert np.abs(f3[0] - fo[0]).max() < FOCK_TOL  # routec_fock_jk
+    assert np.abs(f3[1] - fo[0]).max() < FOCK_TOL  # oqpb_fock
+    assert np.abs(f3[2] - fo[0]).max() < FOCK_TOL  # multi-device context (or a copy on a 1-GPU box)
+    assert abs(nskipped - st["nschwz"]) <= 2       # device Schwarz matrix: ulp-level differences only
+    print(r.stdout.strip())
