@@ -2364,6 +2364,8 @@ eri_group_kernel(const EriArgs A) {
   }
 }
 
+#include "eri_kown.cuh"
+
 // cudaFuncSetAttribute is per device: remember per (kernel instantiation, device) whether the opt-in is done
 struct DevFlags {
   bool done[64] = {};
@@ -2493,6 +2495,39 @@ cudaError_t launch_eri_run(const EriArgs& args, int nblocks, cudaStream_t st) {
     return cudaErrorNotSupported;
   }
 }
+// ket-owner group kernel launch; cudaErrorNotSupported for classes it does not cover
+template <int LA, int LB, int LC, int LD, int PV>
+cudaError_t launch_eri_kown(const EriArgs& args, int nblocks, cudaStream_t st) {
+  using KC = KownCfg<LA, LB, LC, LD, PV>;
+  if constexpr (KC::OK) {
+    static DevFlags flags;
+    bool& attr_set = flags.cur();
+    if (!attr_set && KC::SMEM > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(eri_kown_kernel<LA, LB, LC, LD, PV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KC::SMEM);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    eri_kown_kernel<LA, LB, LC, LD, PV><<<nblocks, KC::NT, KC::SMEM, st>>>(args);
+    return cudaGetLastError();
+  } else {
+    return cudaErrorNotSupported;
+  }
+}
+template <int LA, int LB, int LC, int LD, int PV>
+constexpr int class_kown_qpb() {
+  using KC = KownCfg<LA, LB, LC, LD, PV>;
+  return KC::OK ? KC::WPC * KC::QPW : 0;
+}
+// classes that use the ket-owner kernel by default (OQPB_KOWN=2: every class it covers, 0: none); measured on (H2O)32/cc-pVTZ
+template <int LA, int LB, int LC, int LD>
+constexpr bool class_kown_default() {
+  constexpr int key = LA * 1000 + LB * 100 + LC * 10 + LD;
+  // per-class A/B against the bra-owner group kernel / the thread-per-quartet kernels (gpurun_out/s8_class_w32_*.txt):
+  // the classes with >= 160 Cartesian integrals and a ket of p or d shells win 12-60 %
+  return key == 2111 || key == 2220 || key == 2221 || key == 3121 || key == 3131 || key == 3221 || key == 3220 || key == 3211 ||
+         key == 3231;
+}
+
 template <int LA, int LB, int LC, int LD>
 constexpr bool class_has_run() {
 #ifdef OQPB_RUN_SMALL_ONLY
@@ -2519,7 +2554,7 @@ constexpr int class_max_ctas() {
 }
 
 using LaunchFn = cudaError_t (*)(const EriArgs&, int, cudaStream_t);
-struct ClassEntry { LaunchFn launch; int qpb; int nt; size_t smem; int maxcta; LaunchFn launch_wpq; LaunchFn launch_run; };
+struct ClassEntry { LaunchFn launch; int qpb; int nt; size_t smem; int maxcta; LaunchFn launch_wpq; LaunchFn launch_run; LaunchFn launch_kown; int kown_qpb; bool kown_default; };
 // class table: [pure variant PV = (d pure) | (f pure) << 1][quartet class]
 const ClassEntry* class_table(int pv);
 

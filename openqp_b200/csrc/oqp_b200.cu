@@ -171,6 +171,7 @@ struct oqpb_ctx {
   int nlanes = 4;      // OQPB_NLANES
   int grid_pct = 100;  // OQPB_GRID_PCT: scales the per-class grid caps
   bool use_run = true;   // OQPB_RUN=0: task kernels only
+  int use_kown = 1;      // OQPB_KOWN: 0 = never the ket-owner group kernel, 1 = the classes it wins (default), 2 = every class it covers
   int run_max_bucket_sum = 2;  // OQPB_RUN_BUCKETS
   size_t wpq_max_tasks = 16384;  // OQPB_WPQ_MAX: largest launch (candidate quartets) that uses the warp-per-quartet kernels
   cudaEvent_t fork_ev = nullptr;
@@ -757,8 +758,10 @@ int schwarz(oqpb_ctx* ctx, double mu, std::vector<double>& Qout) {
     A.mode = MODE_SCHWARZ;
     A.qout = d_q.as<double>() + T.cls_off[pc];
     const ClassEntry& ce = tab[quartet_class(pc_of(pc), pc_of(pc))];
-    int nb = std::min((n + ce.qpb - 1) / ce.qpb, 148 * 16);
-    CK(ce.launch(A, nb, ctx->stream));
+    const bool kown = ce.launch_kown != nullptr && (ctx->use_kown >= 2 || (ctx->use_kown == 1 && ce.kown_default));
+    const int qpb = kown ? ce.kown_qpb : ce.qpb;
+    int nb = std::min((n + qpb - 1) / qpb, 148 * 16);
+    CK((kown ? ce.launch_kown : ce.launch)(A, nb, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));  // tasks vector lifetime
   }
   std::vector<double> q(nent);
@@ -949,7 +952,8 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     const bool wpq = ce.launch_wpq != nullptr && ch.cand <= ctx->wpq_max_tasks && (ch.pca % NBK >= 2 || ch.pcb % NBK >= 2);
     // measured on (H2O)32/cc-pVTZ per contraction bucket pair: the run kernels win 9-10 % where both pairs have few
     // primitives (buckets 0/1), are neutral at (0,2) / (2,0) / (1,1) and lose 7-40 % on the heavily contracted launches
-    const bool run = run_ok && !wpq && ce.launch_run != nullptr && (ch.pca % NBK) + (ch.pcb % NBK) <= ctx->run_max_bucket_sum;
+    const bool kown = !wpq && ce.launch_kown != nullptr && (ctx->use_kown >= 2 || (ctx->use_kown == 1 && ce.kown_default));
+    const bool run = run_ok && !wpq && !kown && ce.launch_run != nullptr && (ch.pca % NBK) + (ch.pcb % NBK) <= ctx->run_max_bucket_sum;
     int2* d_items = run ? ctx->d_items[ln].as<int2>() : nullptr;
     size_t ci = cp_index(ch.pca, ch.pcb);
     int offa = T.cls_off[ch.pca], offb = T.cls_off[ch.pcb];
@@ -984,14 +988,14 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     A.Pgen = S.Pgen; A.Fgen = S.Fgen; A.gen_nmat_total = S.gen_nm; A.gen_ncoul = S.gen_ncoul; A.gen_nvec = S.gen_nvec;
     A.gen_mcount = S.gen_mcount >= 0 ? S.gen_mcount : S.gen_nm;
     A.gen_xoff = S.gen_xoff;
-    const size_t tasks_per_cta = wpq ? 4 : (size_t)ce.qpb;
+    const size_t tasks_per_cta = wpq ? 4 : (kown ? (size_t)ce.kown_qpb : (size_t)ce.qpb);
     // run kernels: a warp = an item; the item count is bounded by candidates / RUN_LEN + one per bra, a warp's mean load by
     // the survivor count: size the grid like the task kernel's (one thread per candidate quartet)
     size_t nb = std::min<size_t>((ch.cand + tasks_per_cta - 1) / tasks_per_cta, (size_t)ce.maxcta * ctx->grid_pct / 100);
     if (run) nb = std::min<size_t>(nb, (ch.cand / RUN_LEN + (size_t)nbra + ce.qpb / 32 - 1) / (ce.qpb / 32) + 1);
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (ctx->profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, cs); }
-    CK((run ? ce.launch_run : (wpq ? ce.launch_wpq : ce.launch))(A, (int)std::max<size_t>(nb, 1), cs));
+    CK((kown ? ce.launch_kown : (run ? ce.launch_run : (wpq ? ce.launch_wpq : ce.launch)))(A, (int)std::max<size_t>(nb, 1), cs));
     if (ctx->profile) {
       cudaEventRecord(pe1, cs);
       cudaEventSynchronize(pe1);
@@ -1179,6 +1183,7 @@ int oqpb_ctx_create(oqpb_ctx** out, int device) {
   if (const char* e = getenv("OQPB_NLANES")) ctx->nlanes = std::max(1, std::min((int)oqpb_ctx::NSTREAM, atoi(e)));
   if (const char* e = getenv("OQPB_GRID_PCT")) ctx->grid_pct = std::max(10, atoi(e));
   if (const char* e = getenv("OQPB_RUN")) ctx->use_run = atoi(e) != 0;
+  if (const char* e = getenv("OQPB_KOWN")) ctx->use_kown = atoi(e);
   if (const char* e = getenv("OQPB_RUN_BUCKETS")) ctx->run_max_bucket_sum = atoi(e);
   if (const char* e = getenv("OQPB_WPQ_MAX")) ctx->wpq_max_tasks = (size_t)std::max(0, atoi(e));
   if (const char* e = getenv("OQPB_TASK_CAP_LOG2")) ctx->task_cap = (size_t)1 << std::max(16, std::min(28, atoi(e)));
@@ -2074,7 +2079,8 @@ int oqpb_eri_block(oqpb_ctx* ctx, int i, int j, int k, int l, double* out, int* 
   A.mode = MODE_BLOCK;
   A.blockout = d_out.as<double>();
   const ClassEntry& ce = class_table(ctx->pure_l[2] | (ctx->pure_l[3] << 1))[quartet_class(pc_of(pca), pc_of(pcb))];
-  CK(ce.launch(A, 1, ctx->stream));
+  const bool kown = ce.launch_kown != nullptr && (ctx->use_kown >= 2 || (ctx->use_kown == 1 && ce.kown_default));
+  CK((kown ? ce.launch_kown : ce.launch)(A, 1, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   // kernel block order: (A,B,C,D) = (bra.sa, bra.sb, ket.sa, ket.sb); map back to the caller's (i,j,k,l)
   const PairEntry& pb = T.ent[T.cls_off[pca] + ea];
