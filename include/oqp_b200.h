@@ -196,6 +196,23 @@ void routec_fock_jk(const double* d, double* f, const int* nbf, const int* nfock
 int oqpb_set_default_ctx(oqpb_ctx* ctx);
 int oqpb_set_default_scftype(int urohf);
 
+/* ---- MRSF sigma session, identical signatures to source/modules/routec_sig.F90:28-56 ---------------- */
+/* Replaces the reference's per-iteration triple  mrsfcbc -> int2_mrsf_data_t run -> mrsfmntoia + mrsfesum
+ * (tdhf_mrsf_lib.F90:940-1273, 218-333, 1463-1735, 1918-2036; caller and gate modules/tdhf_mrsf_energy.F90:648-713)
+ * with one device call: trial amplitudes in, (A-B) X out, nothing else crosses the bus.  The session runs on the context
+ * registered with oqpb_set_default_ctx (basis, cutoff and screening set; the reference raises the response cutoff to
+ * max(int2e_cutoff, 1e-8) first, tdhf_mrsf_energy.F90:516-519).
+ *   init: nbf, MO coefficients mo_a / mo_b (nbf, nbf) and MO-basis Fock matrices fmo_a / fmo_b (nbf, nbf), column-major;
+ *         nocca, noccb = nocca - 2; kind 1 = singlet, 3 = triplet response.  Returns 0 when the session is ready.
+ *   set_scale: exact-exchange scale of the response (scale_exchange = scale_coulomb of int2_mrsf_data_t).
+ *   iter: bvec_mo (ntrial, nv_new) -> sigma_mo (ntrial, nv_new), ntrial = nocca (nbf - noccb), occupied index fastest;
+ *         info = 0 on success, anything else tells the caller to take its native path (as the reference does).         */
+int  routec_sig_init(const int* nbf, const double* mo_a, const double* mo_b, const double* fmo_a, const double* fmo_b,
+                     const int* nocca, const int* noccb, const int* kind);
+void routec_sig_set_scale(const double* s);
+void routec_sig_iter(const double* bvec_mo, const int* nv_new, double* sigma_mo, int* info);
+void routec_sig_free(void);
+
 #ifdef __cplusplus
 }
 #endif

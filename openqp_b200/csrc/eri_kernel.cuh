@@ -59,6 +59,9 @@
 #ifndef OQPB_RUN_M
 #define OQPB_RUN_M 7
 #endif
+#ifndef OQPB_RUN_SEGC
+#define OQPB_RUN_SEGC 1
+#endif
 #ifndef OQPB_REGVRR_MAX
 #define OQPB_REGVRR_MAX 64
 #endif
@@ -1962,8 +1965,8 @@ eri_run_kernel(const EriArgs A) {
       }
       st_ints += (unsigned long long)nz * (unsigned)(8.0f * facf);
       SegMask mc;
-      if constexpr (!GS) mc = seg_make(act ? (long long)pk.sa : -1 - (long long)lane, lane);  // runs of equal ket shell c
-      digest_run<N0, N1, N2, N3, !GS>(A, blk, dab, pb.oa, pb.ob, pk.oa, pk.ob, jab, mc);
+      if constexpr (!GS && OQPB_RUN_SEGC) mc = seg_make(act ? (long long)pk.sa : -1 - (long long)lane, lane);  // runs of equal ket shell c
+      digest_run<N0, N1, N2, N3, !GS && OQPB_RUN_SEGC>(A, blk, dab, pb.oa, pb.ob, pk.oa, pk.ob, jab, mc);
     }
     // J_ab of the whole run: butterfly over the lanes, lane (e mod 32) issues the red of element e
 #pragma unroll

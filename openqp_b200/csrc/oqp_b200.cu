@@ -2186,3 +2186,5 @@ void routec_fock_jk(const double* d, double* f, const int* nbf, const int* nfock
 }
 
 }  // extern "C"
+
+#include "sigma_session.cuh"

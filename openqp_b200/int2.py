@@ -478,3 +478,49 @@ def jk(drv: Int2Compute, P, want_j=None, want_k=None):
     ns = C.c_longlong(0)
     drv._check(lib().oqpb_jk(drv._h, C.c_int(n), _dp(PF), _ip(wj), _ip(wk), _dp(J), _dp(K), C.byref(ns)), "oqpb_jk")
     return np.transpose(J, (0, 2, 1)).copy(), np.transpose(K, (0, 2, 1)).copy(), int(ns.value)
+
+
+class RoutecSig:
+    """Host-side mirror of the reference's `routec_sig` module (source/modules/routec_sig.F90:204-252): the MRSF Davidson
+    sigma session  routec_sig_begin -> routec_sig_apply (per iteration) -> routec_sig_end  on the device.  `drv` must be
+    initialised (basis, cutoff, screening); it is registered as the library's default context like the legacy seam."""
+
+    def __init__(self, drv: Int2Compute):
+        self.drv = drv
+        self.active = False
+
+    def begin(self, mo_a, mo_b, fa, fb, nocca, noccb, mrst, scale=1.0):
+        """routec_sig_begin (routec_sig.F90:204-219): MO coefficients [mu, p], MO-basis Fock matrices, mrst 1 / 3.
+        Returns the library's error code (0 = the session is ready)."""
+        L = lib()
+        L.oqpb_set_default_ctx(self.drv._h)
+        nbf = self.drv.basis.nbf
+        mats = [np.asfortranarray(np.asarray(m, dtype=np.float64)) for m in (mo_a, mo_b, fa, fb)]
+        for m in mats:
+            assert m.shape == (nbf, nbf)
+        kind = 3 if mrst == 3 else 1
+        rc = L.routec_sig_init(C.byref(C.c_int(nbf)), *[m.ctypes.data_as(C.POINTER(C.c_double)) for m in mats],
+                               C.byref(C.c_int(nocca)), C.byref(C.c_int(noccb)), C.byref(C.c_int(kind)))
+        if rc == 0:
+            L.routec_sig_set_scale(C.byref(C.c_double(scale)))
+            self.active = True
+            self.ntrial = nocca * (nbf - noccb)
+        return int(rc)
+
+    def apply(self, bvec_mo):
+        """routec_sig_apply (routec_sig.F90:221-241): bvec_mo (ntrial, nv) -> sigma (ntrial, nv) = (A-B) X, or None when the
+        library declines (the reference then reverts to its native path)."""
+        if not self.active:
+            raise Int2Error("routec_sig: no session")
+        b = np.asfortranarray(np.asarray(bvec_mo, dtype=np.float64))
+        assert b.ndim == 2 and b.shape[0] == self.ntrial
+        out = np.zeros_like(b, order="F")
+        info = C.c_int(1)
+        lib().routec_sig_iter(b.ctypes.data_as(C.POINTER(C.c_double)), C.byref(C.c_int(b.shape[1])),
+                              out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(info))
+        return out if info.value == 0 else None
+
+    def end(self):
+        """routec_sig_end (routec_sig.F90:243-245)"""
+        lib().routec_sig_free()
+        self.active = False

@@ -29,6 +29,12 @@ def energies():
         out[key] = {"energy": d["energy"], "source": path}
     d = json.load(open(os.path.join(REF, "examples/TDHF/H2O_TDHF_ENERGY.json")))
     out["h2o_tdhf_631gd"] = {"energy": d["energy"], "td_energies": d["td_energies"], "source": "examples/TDHF/H2O_TDHF_ENERGY.json"}
+    # MRSF-CIS (no functional) on an ROHF triplet: the only XC-free MRSF deck; pins int2_mrsf_data_t and the sigma triple.
+    # roots_nstate20: the tighter-converged roots quoted in the deck's own header comment (nstate=20 reference run)
+    path = "examples/MRSF-TDDFT/CH2O_MRSFTDDFT_SYMMETRY_BLOCK_COVERAGE.json"
+    d = json.load(open(os.path.join(REF, path)))
+    out["ch2o_mrsf_triplet_631g"] = {"energy": d["energy"], "td_energies": d["td_energies"], "atoms": d["atoms"], "coord": d["coord"],
+                                     "roots_nstate20": [-0.00500108, 0.07496767, 0.17574606, 0.23436551], "source": path}
     json.dump(out, open(os.path.join(HERE, "reference_energies.json"), "w"), indent=1)
 
 

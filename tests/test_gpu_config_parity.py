@@ -13,7 +13,7 @@ Tolerances as everywhere: quartet counts exact, Fock / f3 elements 1e-10 Eh abso
 import numpy as np
 import pytest
 
-from common import decaying_density, random_sym_density
+from common import decaying_density, golden, random_sym_density
 from openqp_b200 import basis as B
 from openqp_b200.scf import pack, scf
 
@@ -253,3 +253,102 @@ def test_multi_device_context(oracle_mod):
     assert np.abs(g3.f3 - r3.f3).max() < 1e-11 and g3.skipped == r3.skipped
     one.clean()
     two.clean()
+
+
+def test_sigma_session_ch2o_golden(oracle_mod, drv):
+    """routec_sig_init / _set_scale / _iter / _free (routec_sig.F90:28-56) against the reference's XC-free MRSF golden
+    (examples/MRSF-TDDFT/CH2O_MRSFTDDFT_SYMMETRY_BLOCK_COVERAGE.json): the device session applied to unit vectors gives the
+    full (A-B) matrix; its lowest eigenvalues are the reference's triplet MRSF-CIS excitation energies, and every sigma
+    vector agrees with the CPU restatement (oracle/mrsf_sigma.py) to 1e-10.  Singlet kind: device vs restatement."""
+    from oracle import mrsf_sigma as MS
+    from openqp_b200.int2 import RoutecSig
+    g = golden("reference_energies.json")["ch2o_mrsf_triplet_631g"]
+    mol = B.Molecule(np.array(g["atoms"]), np.array(g["coord"]).reshape(-1, 3))
+    bs = B.BasisSet(mol, "6-31g")
+    o = oracle_mod.Oracle(bs, 1e-12)
+    q = o.set_screening()
+    drv.init(bs, 1e-12)
+    drv.set_screening(q)
+    S, T, V = o.int1e()
+    nel = int(sum(g["atoms"]))
+    na, nb = nel // 2 + 1, nel // 2 - 1
+    # the ROHF reference state through the GPU Fock builder
+    from openqp_b200.int2 import fock_jk
+    e, Cm, eps, Fa, Fb = MS.rohf(bs.nbf, S, T + V, mol.nuclear_repulsion(), lambda dp: fock_jk(drv, dp, urohf=True)[0], na, nb)
+    assert abs(e - g["energy"]) < 1e-8, (e, g["energy"])
+    fa, fb = Cm.T @ Fa @ Cm, Cm.T @ Fb @ Cm
+    n = bs.nbf
+    ntrial = na * (n - nb)
+    jk = lambda d3, sx: o.mrsf(d3, scale_exchange=sx, scale_coulomb=sx)[0]
+    sig = RoutecSig(drv)
+    for mrst in (3, 1):
+        assert sig.begin(Cm, Cm, fa, fb, na, nb, mrst, 1.0) == 0
+        keep = np.array([k for k in range(ntrial) if k not in set(MS.excluded_amplitudes(na, nb, n, mrst))])
+        A = np.zeros((ntrial, len(keep)))
+        worst = 0.0
+        for k0 in range(0, len(keep), 40):
+            ks = keep[k0:k0 + 40]
+            E = np.zeros((ntrial, len(ks)))
+            E[ks, np.arange(len(ks))] = 1.0
+            sg = sig.apply(E)
+            assert sg is not None
+            so = MS.sigma(E, Cm, Cm, fa, fb, na, nb, mrst, jk)
+            worst = max(worst, np.abs(sg - so).max())
+            A[:, k0:k0 + len(ks)] = sg
+        sig.end()
+        assert worst < 1e-10, worst
+        # a random (non-unit) batch as well: every amplitude block is exercised at once
+        rng = np.random.default_rng(5)
+        Xr = rng.normal(size=(ntrial, 5))
+        assert sig.begin(Cm, Cm, fa, fb, na, nb, mrst, 1.0) == 0
+        sg = sig.apply(Xr)
+        sig.end()
+        so = MS.sigma(Xr, Cm, Cm, fa, fb, na, nb, mrst, jk)
+        assert np.abs(sg - so).max() < 1e-9 * max(1.0, np.abs(so).max()), np.abs(sg - so).max()
+        A = A[keep]
+        w = np.linalg.eigvalsh(0.5 * (A + A.T))
+        print(f"CH2O MRSF-CIS mrst={mrst}: roots {w[:4]}  max|sigma_gpu - sigma_oracle| = {worst:.2e}")
+        if mrst == 3:
+            assert np.allclose(w[:4], g["roots_nstate20"], atol=2e-8), (w[:4], g["roots_nstate20"])
+            assert np.allclose(w[:3], g["td_energies"], atol=5e-7), (w[:3], g["td_energies"])
+    # no session: the call declines and the caller keeps its native path (info != 0)
+    assert sig.active is False
+    import ctypes
+    from openqp_b200.int2 import lib
+    info = ctypes.c_int(0)
+    x = np.zeros((ntrial, 1)); y = np.zeros((ntrial, 1))
+    lib().routec_sig_iter(x.ctypes.data_as(ctypes.c_void_p), ctypes.byref(ctypes.c_int(1)), y.ctypes.data_as(ctypes.c_void_p),
+                          ctypes.byref(info))
+    assert info.value != 0
+
+
+def test_sigma_session_c5(oracle_mod, drv):
+    """config 5 molecule (C20NOH22 / 6-31G(d), 374 bf) at the reference's response cutoff 1e-8 (types.F90:185): three trial
+    vectors through the device session against the CPU restatement around the oracle's int2_mrsf_data_t.  Orbitals and MO
+    Fock matrices are synthetic (orthonormalised random / symmetric random): the sigma step is linear algebra around the
+    J/K build and does not need a converged reference state."""
+    from oracle import mrsf_sigma as MS
+    from openqp_b200.int2 import RoutecSig
+    mol, bs, o = _setup(oracle_mod, drv, "c5")
+    o.set_cutoff(1e-8)
+    drv.set_cutoff(1e-8)
+    n = bs.nbf
+    rng = np.random.default_rng(11)
+    S = o.int1e()[0]
+    s, U = np.linalg.eigh(S)
+    Cm = (U @ np.diag(s ** -0.5) @ U.T) @ np.linalg.qr(rng.normal(size=(n, n)))[0]
+    fa = rng.normal(size=(n, n)) * 0.1; fa = fa + fa.T + np.diag(np.linspace(-10, 3, n))
+    fb = rng.normal(size=(n, n)) * 0.1; fb = fb + fb.T + np.diag(np.linspace(-10, 3, n))
+    nel = int(sum(mol.Z))
+    na, nb = nel // 2 + 1, nel // 2 - 1
+    ntrial = na * (n - nb)
+    X = rng.normal(size=(ntrial, 3)) * np.exp(-rng.uniform(0, 6, size=(ntrial, 1)))
+    sig = RoutecSig(drv)
+    assert sig.begin(Cm, Cm, fa, fb, na, nb, 1, 0.5) == 0
+    sg = sig.apply(X)
+    sig.end()
+    assert sg is not None
+    so = MS.sigma(X, Cm, Cm, fa, fb, na, nb, 1, lambda d3, sx: o.mrsf(d3, scale_exchange=sx, scale_coulomb=sx)[0], 0.5)
+    err = np.abs(sg - so).max()
+    print(f"c5 sigma session: ntrial {ntrial}, max|sigma| {np.abs(so).max():.3f}, max|d sigma| {err:.2e}")
+    assert err < 1e-9 * max(1.0, np.abs(so).max()), err

@@ -268,3 +268,32 @@ def test_oracle_gradient_response_consumers_vs_dense_eri(oracle_mod):
                 if cur_pass == 2 and c < 10:
                     ref = 0.0 * ref
                 assert np.abs(f3[v, c] - ref).max() < 1e-13
+
+
+def _ch2o_rohf(oracle_mod):
+    g = golden("reference_energies.json")["ch2o_mrsf_triplet_631g"]
+    mol = B.Molecule(np.array(g["atoms"]), np.array(g["coord"]).reshape(-1, 3))
+    bs = B.BasisSet(mol, "6-31g")
+    o = oracle_mod.Oracle(bs, cutoff=1e-12)
+    o.set_screening()
+    S, T, V = o.int1e()
+    nel = int(sum(g["atoms"]))
+    na, nb = nel // 2 + 1, nel // 2 - 1
+    from oracle import mrsf_sigma as MS
+    e, C, eps, Fa, Fb = MS.rohf(bs.nbf, S, T + V, mol.nuclear_repulsion(), lambda dp: o.fock(dp, urohf=True)[0], na, nb)
+    return g, bs, o, MS, e, C, C.T @ Fa @ C, C.T @ Fb @ C, na, nb
+
+
+def test_mrsf_ch2o_golden(oracle_mod):
+    """examples/MRSF-TDDFT/CH2O_MRSFTDDFT_SYMMETRY_BLOCK_COVERAGE.json: ROHF triplet + MRSF-CIS/6-31G triplet roots with NO
+    functional -- the XC-free MRSF golden.  Pins int2_mrsf_data_t (tdhf_mrsf_lib.F90:218-333) and the sigma triple
+    mrsfcbc / mrsfmntoia / mrsfesum (oracle/mrsf_sigma.py) to the real binary: the full (A-B) matrix is built by applying
+    the sigma step to unit vectors and diagonalised.  The deck's JSON holds Davidson-converged roots (residual 1e-8 in
+    ||r||^2, i.e. ~1e-6 Eh on a root); its header quotes the tighter nstate=20 run, which the dense solve reproduces."""
+    g, bs, o, MS, e, C, fa, fb, na, nb = _ch2o_rohf(oracle_mod)
+    assert abs(e - g["energy"]) < 1e-8, (e, g["energy"])
+    A, asym = MS.dense_response_matrix(C, C, fa, fb, na, nb, 3, lambda d3, sx: o.mrsf(d3, scale_exchange=sx, scale_coulomb=sx)[0])
+    assert asym < 1e-10  # (A-B) is symmetric on the Davidson's amplitude space
+    w = np.linalg.eigvalsh(A)
+    assert np.allclose(w[:4], g["roots_nstate20"], atol=2e-8), (w[:4], g["roots_nstate20"])
+    assert np.allclose(w[:3], g["td_energies"], atol=5e-7), (w[:3], g["td_energies"])
