@@ -59,6 +59,9 @@
 #ifndef OQPB_RUN_M
 #define OQPB_RUN_M 7
 #endif
+#ifndef OQPB_MED_VOLATILE
+#define OQPB_MED_VOLATILE 0
+#endif
 #ifndef OQPB_RUN_SEGC
 #define OQPB_RUN_SEGC 1
 #endif
@@ -1606,7 +1609,13 @@ __device__ __forceinline__ void eval_quartet_thread(const EriArgs& A, const Pair
           constexpr int ix = (Cart<LA>::x(ia) * (LB + 1) + Cart<LB>::x(ib)) * NKL1 + Cart<LC>::x(ic) * (LD + 1) + Cart<LD>::x(id);
           constexpr int iy = (Cart<LA>::y(ia) * (LB + 1) + Cart<LB>::y(ib)) * NKL1 + Cart<LC>::y(ic) * (LD + 1) + Cart<LD>::y(id);
           constexpr int iz = (Cart<LA>::z(ia) * (LB + 1) + Cart<LB>::z(ib)) * NKL1 + Cart<LC>::z(ic) * (LD + 1) + Cart<LD>::z(id);
+#if OQPB_MED_VOLATILE
+          // real shared-memory loads: without `volatile` ptxas forwards the stored table values and keeps all 3*G3 of them
+          // in registers next to the NCART4 accumulators (spills above ~100 accumulators)
+          if constexpr (GS) { const volatile double* gv = gcol; acc[e] = fma(gv[ix * NTH] * gv[(G3 + iy) * NTH], gv[(2 * G3 + iz) * NTH], acc[e]); }
+#else
           if constexpr (GS) acc[e] = fma(gcol[ix * NTH] * gcol[(G3 + iy) * NTH], gcol[(2 * G3 + iz) * NTH], acc[e]);
+#endif
           else acc[e] = fma(g[0][ix] * g[1][iy], g[2][iz], acc[e]);
         });
       }

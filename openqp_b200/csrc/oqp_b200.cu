@@ -129,7 +129,8 @@ double fprim_model(int l1, int l2, int l3, int l4) {
 // Work plan of a build: per (bra list, ket list) the ket bound index of every bra of this rank and the launch chunks.
 // It depends on the density only through 4*max|D| rounded UP to a power of two (a larger bound only admits more
 // candidates to the exact test in k_enum), so consecutive SCF iterations reuse it: no host planning, no upload.
-struct PlanChunk { int pca, pcb, p0, p1; size_t cand; };
+struct PlanChunk { int pca, pcb, p0, p1; size_t cand; int nr, rk; };  // nr / rk: bra stride and offset of this chunk (rank split, or 1 / 0 for a
+                                                                       // list pair given to one rank as a whole)
 struct BuildPlan {
   bool valid = false;
   double bound4 = -1.0;
@@ -171,6 +172,7 @@ struct oqpb_ctx {
   int nlanes = 4;      // OQPB_NLANES
   int grid_pct = 100;  // OQPB_GRID_PCT: scales the per-class grid caps
   bool use_run = true;   // OQPB_RUN=0: task kernels only
+  double whole_ms = 1.0;   // OQPB_WHOLE_MS: list pairs with a shorter per-rank share go to one rank as a whole (0 = always split)
   int use_kown = 1;      // OQPB_KOWN: 0 = never the ket-owner group kernel, 1 = the classes it wins (default), 2 = every class it covers
   int run_max_bucket_sum = 2;  // OQPB_RUN_BUCKETS
   size_t wpq_max_tasks = 16384;  // OQPB_WPQ_MAX: largest launch (candidate quartets) that uses the warp-per-quartet kernels
@@ -835,14 +837,60 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   int rc;
   double t_planned = tnow(), t_uploaded = t_planned;
   size_t km_count = 0;
-  if (!(P.valid && P.gen == ctx->plan_gen && P.bound4 == bound4p)) {
+  // A cached plan stays usable while its density bound is an UPPER bound that is not too loose: kets beyond the bound
+  // index of a larger bound cannot survive a smaller one either, and k_enum applies the exact test.  Within 4 binades the
+  // extra candidates cost < 2 % of a build; the default incremental SCF (dD shrinks every iteration) then re-plans every
+  // third or fourth iteration instead of every iteration.
+  if (!(P.valid && P.gen == ctx->plan_gen && P.bound4 >= bound4p && P.bound4 <= 16.0 * bound4p)) {
     P.valid = false;
     P.chunks.clear(); P.cps.clear(); P.km_off.clear(); P.total_local = 0;
     std::vector<std::vector<int>> kmax_all;  // index by list pair order
+    std::vector<double> rank_load(std::max(1, ctx->nranks), 0.0);
     // OQPB_ONLY="a,b": profiling knob, build only the (bra list a, ket list b) launches (list = class * 4 + bucket)
     static const char* only_env = getenv("OQPB_ONLY");
     int only_a = -1, only_b = -1;
     if (only_env) sscanf(only_env, "%d,%d", &only_a, &only_b);
+    // Several ranks: every launch carries a fixed tail (the last, partly filled wave), so dealing 1/N of EVERY list pair to
+    // every rank makes N times as many small launches: measured 4 % of the per-rank time at N = 8 on (H2O)32.  List pairs
+    // whose per-rank share would be short are therefore given to ONE rank as a whole, each to the rank with the least
+    // estimated load so far.  Every rank computes the same assignment (the estimate uses the candidates of
+    // every 8th bra of the list, whatever the rank).
+    std::vector<int> owner_of((size_t)NL * NL, -1);  // -1: split over the ranks
+    if (nr > 1 && ctx->whole_ms > 0) {
+      // cost model fitted to the per-(class, contraction bucket pair) profile of (H2O)32/cc-pVTZ (profiles/): SM-ns per
+      // quartet = 15 + 0.8 N + prims (2 + 0.35 N), N = Cartesian integrals of the class, prims = primitive quartets that
+      // pass the int_rys.F90:232 test (typical value per bucket pair)
+      static const double prims_tab[4][4] = {{1, 3.1, 8, 28}, {3.1, 7.4, 18.4, 67}, {8, 18.4, 49, 183}, {28, 67, 183, 745}};
+      std::vector<std::pair<double, int>> whole;
+      for (int pca = 0; pca < NL; ++pca) {
+        const int na = T.cls_off[pca + 1] - T.cls_off[pca];
+        for (int pcb = 0; pcb <= pca && na > 0; ++pcb) {
+          const int nb = T.cls_off[pcb + 1] - T.cls_off[pcb];
+          if (nb == 0) continue;
+          const double* Qa = hQ.data() + T.cls_off[pca];
+          const double* Qs = hQsuf.data() + T.cls_off[pcb];
+          double est = 0;
+          for (int p = 0; p < na; p += 8) {
+            int lo = 0, hi = nb;
+            while (lo < hi) { int mid = (lo + hi) / 2; if ((Qa[p] * Qs[mid]) * bound4p < cutoff) hi = mid; else lo = mid + 1; }
+            est += pca == pcb ? std::min(lo, p + 1) : lo;
+          }
+          const int pa_ = pc_of(pca), pb_ = pc_of(pcb);
+          const double ncart4 = (double)ncart(PC_LA[pa_]) * ncart(PC_LB[pa_]) * ncart(PC_LA[pb_]) * ncart(PC_LB[pb_]);
+          const double prims = prims_tab[pca % NBK][pcb % NBK];
+          const double est_ms = est * std::min(8, na) * (15.0 + 0.8 * ncart4 + prims * (2.0 + 0.35 * ncart4)) / 148.0 * 1e-6;
+          if (est_ms < ctx->whole_ms * nr) whole.push_back({est_ms, pca * NL + pcb});
+        }
+      }
+      // (in list order: sorting longest-first was measured WORSE, 1.04-1.10 max/mean instead of 1.01-1.02 -- the model's errors
+      // are correlated inside a class, and the list order interleaves the classes)
+      for (const auto& w : whole) {
+        int owner = 0;
+        for (int r = 1; r < nr; ++r) if (rank_load[r] < rank_load[owner]) owner = r;
+        rank_load[owner] += w.first;
+        owner_of[w.second] = owner;
+      }
+    }
     for (int pca = 0; pca < NL; ++pca) {  // pca / pcb are pair LISTS here (class x contraction bucket)
       int na = T.cls_off[pca + 1] - T.cls_off[pca];
       if (na == 0) continue;
@@ -854,31 +902,38 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
         std::vector<int> km(na, 0);
         // kets at or beyond km[p] cannot survive: suffix maxima of the ket list's bounds are monotone
         const double* Qs = hQsuf.data() + T.cls_off[pcb];
-#pragma omp parallel for schedule(static) if (na > 4096)
-        for (int p = rk; p < na; p += nr) {  // this rank's bras only
+        const bool diag = pca == pcb;
+        auto kbound = [&](int p) {
           int lo = 0, hi = nb;  // first k with Qa[p] * Qs[k] * bound4p < cutoff
           while (lo < hi) {
             int mid = (lo + hi) / 2;
             if ((Qa[p] * Qs[mid]) * bound4p < cutoff) hi = mid; else lo = mid + 1;
           }
-          km[p] = lo;
+          return lo;
+        };
+        int nr_ = nr, rk_ = rk;
+        const int owner = owner_of[(size_t)pca * NL + pcb];
+        if (owner >= 0) {  // this list pair belongs to one rank as a whole
+          if (owner != rk) continue;
+          nr_ = 1; rk_ = 0;
         }
+#pragma omp parallel for schedule(static) if (na > 4096)
+        for (int p = rk_; p < na; p += nr_) km[p] = kbound(p);  // this rank's bras only
         // chunking over this rank's bras (p % nranks == rank)
         size_t cand = 0;
         int p0 = 0;
-        bool diag = pca == pcb;
         for (int p = 0; p < na; ++p) {
-          if (p % nr != rk) continue;
+          if (p % nr_ != rk_) continue;
           P.total_local += diag ? (p + 1) : nb;
           size_t c = diag ? (size_t)std::min(km[p], p + 1) : (size_t)km[p];
           if (cand + c > ctx->task_cap && cand > 0) {
-            P.chunks.push_back({pca, pcb, p0, p, cand});
+            P.chunks.push_back({pca, pcb, p0, p, cand, nr_, rk_});
             p0 = p;
             cand = 0;
           }
           cand += c;
         }
-        if (cand > 0) P.chunks.push_back({pca, pcb, p0, na, cand});
+        if (cand > 0) P.chunks.push_back({pca, pcb, p0, na, cand, nr_, rk_});
         kmax_all.push_back(std::move(km));
         P.cps.push_back({pca, pcb});
       }
@@ -957,14 +1012,14 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     int2* d_items = run ? ctx->d_items[ln].as<int2>() : nullptr;
     size_t ci = cp_index(ch.pca, ch.pcb);
     int offa = T.cls_off[ch.pca], offb = T.cls_off[ch.pcb];
-    int nbra = (ch.p1 - ch.p0 + nr - 1) / nr + 1;
+    int nbra = (ch.p1 - ch.p0 + ch.nr - 1) / ch.nr + 1;
     // first bra of this rank at or after p0
-    int pstart = ch.p0 + ((rk - ch.p0 % nr) % nr + nr) % nr;
+    int pstart = ch.p0 + ((ch.rk - ch.p0 % ch.nr) % ch.nr + ch.nr) % ch.nr;
     k_enum<<<nbra, ENUM_NT, use_smem ? smem_rows : 0, cs>>>(
         T.d_ent.as<PairEntry>() + offa, T.d_ent.as<PairEntry>() + offb, dQ + offa,
         dQ + offb, ctx->d_d4.as<double>() + offa, ctx->d_d4.as<double>() + offb,
         ctx->d_ok.as<int>() + offa, ctx->d_ok.as<int>() + offb, T.d_canon.as<int>() + offa,
-        T.d_canon.as<int>() + offb, d_km.as<int>() + km_off[ci], pstart, ch.p1, nr, ch.pca == ch.pcb,
+        T.d_canon.as<int>() + offb, d_km.as<int>() + km_off[ci], pstart, ch.p1, ch.nr, ch.pca == ch.pcb,
         ctx->d_dsh.as<double>(), ns, cutoff, d_tasks, d_cnt + 4 * c, (unsigned)ctx->task_cap, use_smem, d_items,
         d_cnt + 4 * c + 2, (unsigned)item_cap);
     CK(cudaGetLastError());
@@ -1184,6 +1239,7 @@ int oqpb_ctx_create(oqpb_ctx** out, int device) {
   if (const char* e = getenv("OQPB_GRID_PCT")) ctx->grid_pct = std::max(10, atoi(e));
   if (const char* e = getenv("OQPB_RUN")) ctx->use_run = atoi(e) != 0;
   if (const char* e = getenv("OQPB_KOWN")) ctx->use_kown = atoi(e);
+  if (const char* e = getenv("OQPB_WHOLE_MS")) ctx->whole_ms = atof(e);
   if (const char* e = getenv("OQPB_RUN_BUCKETS")) ctx->run_max_bucket_sum = atoi(e);
   if (const char* e = getenv("OQPB_WPQ_MAX")) ctx->wpq_max_tasks = (size_t)std::max(0, atoi(e));
   if (const char* e = getenv("OQPB_TASK_CAP_LOG2")) ctx->task_cap = (size_t)1 << std::max(16, std::min(28, atoi(e)));
