@@ -34,7 +34,7 @@ def main():
     if len(sys.argv) > 2 and sys.argv[2] == "--child":
         return child(wl)
     cmd = ["ncu", "--profile-from-start", "off", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum",
-           "--clock-control", "none", "--csv", sys.executable, os.path.abspath(__file__), wl, "--child"]
+           "--clock-control", "none", "--cache-control", "none", "--csv", sys.executable, os.path.abspath(__file__), wl, "--child"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     rows = [l for l in r.stdout.splitlines() if l.startswith('"')]
     build = [l for l in r.stdout.splitlines() if l.startswith("BUILD")]
@@ -56,7 +56,7 @@ def main():
            "launches": n // 2, "by_kernel_family_bytes": {k: v[0] for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])},
            "algorithmic_bytes": 16 * info.get("ntri", 0), "build": info,
            "how": "ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum over the third build "
-                  "(cudaProfilerStart/Stop), summed over every launch of the build; serialised launches, cold L2 between them"}
+                  "(cudaProfilerStart/Stop), summed over every launch of the build; serialised launches, --cache-control none (L2 stays warm between launches as in a real build)"}
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "profiles", f"r02_dram_{wl}.json"), "w"), indent=1)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"r02_dram_{wl}.json"), "w"), indent=1)
