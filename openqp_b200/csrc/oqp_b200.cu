@@ -172,7 +172,7 @@ struct oqpb_ctx {
   int nlanes = 4;      // OQPB_NLANES
   int grid_pct = 100;  // OQPB_GRID_PCT: scales the per-class grid caps
   bool use_run = true;   // OQPB_RUN=0: task kernels only
-  double whole_ms = 1.0;   // OQPB_WHOLE_MS: list pairs with a shorter per-rank share go to one rank as a whole (0 = always split)
+  double whole_ms = 2.5;   // OQPB_WHOLE_MS: a list pair is shared by round(estimated ms / whole_ms) ranks (0 = always by all ranks)
   int use_kown = 1;      // OQPB_KOWN: 0 = never the ket-owner group kernel, 1 = the classes it wins (default), 2 = every class it covers
   int run_max_bucket_sum = 2;  // OQPB_RUN_BUCKETS
   size_t wpq_max_tasks = 16384;  // OQPB_WPQ_MAX: largest launch (candidate quartets) that uses the warp-per-quartet kernels
@@ -851,17 +851,20 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     int only_a = -1, only_b = -1;
     if (only_env) sscanf(only_env, "%d,%d", &only_a, &only_b);
     // Several ranks: every launch carries a fixed tail (the last, partly filled wave), so dealing 1/N of EVERY list pair to
-    // every rank makes N times as many small launches: measured 4 % of the per-rank time at N = 8 on (H2O)32.  List pairs
-    // whose per-rank share would be short are therefore given to ONE rank as a whole, each to the rank with the least
-    // estimated load so far.  Every rank computes the same assignment (the estimate uses the candidates of
-    // every 8th bra of the list, whatever the rank).
-    std::vector<int> owner_of((size_t)NL * NL, -1);  // -1: split over the ranks
+    // every rank makes N times as many small launches: measured 4 % of the per-rank time at N = 8 on (H2O)32.  A list
+    // pair is therefore shared by only s = round(estimated ms / whole_ms) ranks (1 <= s <= N: short pairs go to ONE rank as
+    // a whole, long ones to all), namely the s ranks with the least estimated load so far; among them the bras are dealt
+    // cyclically.  Every rank computes the same assignment (the estimate uses the candidates of every 8th bra of the list,
+    // whatever the rank).
+    std::vector<int> share_s((size_t)NL * NL, nr), share_j((size_t)NL * NL, rk);  // ranks sharing the pair; my index among them (-1: none)
     if (nr > 1 && ctx->whole_ms > 0) {
       // cost model fitted to the per-(class, contraction bucket pair) profile of (H2O)32/cc-pVTZ (profiles/): SM-ns per
       // quartet = 15 + 0.8 N + prims (2 + 0.35 N), N = Cartesian integrals of the class, prims = primitive quartets that
       // pass the int_rys.F90:232 test (typical value per bucket pair)
       static const double prims_tab[4][4] = {{1, 3.1, 8, 28}, {3.1, 7.4, 18.4, 67}, {8, 18.4, 49, 183}, {28, 67, 183, 745}};
-      std::vector<std::pair<double, int>> whole;
+      std::vector<int> order(nr);
+      // (pairs in list order: sorting longest-first was measured WORSE, 1.04-1.10 max/mean instead of 1.01-1.02 -- the model's
+      // errors are correlated inside a class, and the list order interleaves the classes)
       for (int pca = 0; pca < NL; ++pca) {
         const int na = T.cls_off[pca + 1] - T.cls_off[pca];
         for (int pcb = 0; pcb <= pca && na > 0; ++pcb) {
@@ -879,16 +882,21 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
           const double ncart4 = (double)ncart(PC_LA[pa_]) * ncart(PC_LB[pa_]) * ncart(PC_LA[pb_]) * ncart(PC_LB[pb_]);
           const double prims = prims_tab[pca % NBK][pcb % NBK];
           const double est_ms = est * std::min(8, na) * (15.0 + 0.8 * ncart4 + prims * (2.0 + 0.35 * ncart4)) / 148.0 * 1e-6;
-          if (est_ms < ctx->whole_ms * nr) whole.push_back({est_ms, pca * NL + pcb});
+          const int sgl = (int)std::min<double>(nr, std::max(1.0, std::floor(est_ms / ctx->whole_ms + 0.5)));
+          const size_t id = (size_t)pca * NL + pcb;
+          if (sgl >= nr) {
+            for (int r = 0; r < nr; ++r) rank_load[r] += est_ms / nr;
+            continue;
+          }
+          for (int r = 0; r < nr; ++r) order[r] = r;
+          std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return rank_load[a] < rank_load[b]; });
+          share_s[id] = sgl;
+          share_j[id] = -1;
+          for (int j = 0; j < sgl; ++j) {
+            rank_load[order[j]] += est_ms / sgl;
+            if (order[j] == rk) share_j[id] = j;
+          }
         }
-      }
-      // (in list order: sorting longest-first was measured WORSE, 1.04-1.10 max/mean instead of 1.01-1.02 -- the model's errors
-      // are correlated inside a class, and the list order interleaves the classes)
-      for (const auto& w : whole) {
-        int owner = 0;
-        for (int r = 1; r < nr; ++r) if (rank_load[r] < rank_load[owner]) owner = r;
-        rank_load[owner] += w.first;
-        owner_of[w.second] = owner;
       }
     }
     for (int pca = 0; pca < NL; ++pca) {  // pca / pcb are pair LISTS here (class x contraction bucket)
@@ -911,12 +919,9 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
           }
           return lo;
         };
-        int nr_ = nr, rk_ = rk;
-        const int owner = owner_of[(size_t)pca * NL + pcb];
-        if (owner >= 0) {  // this list pair belongs to one rank as a whole
-          if (owner != rk) continue;
-          nr_ = 1; rk_ = 0;
-        }
+        // the ranks that share this list pair and this rank's place among them (see above)
+        const int nr_ = share_s[(size_t)pca * NL + pcb], rk_ = share_j[(size_t)pca * NL + pcb];
+        if (rk_ < 0) continue;
 #pragma omp parallel for schedule(static) if (na > 4096)
         for (int p = rk_; p < na; p += nr_) km[p] = kbound(p);  // this rank's bras only
         // chunking over this rank's bras (p % nranks == rank)
