@@ -352,3 +352,21 @@ def test_sigma_session_c5(oracle_mod, drv):
     err = np.abs(sg - so).max()
     print(f"c5 sigma session: ntrial {ntrial}, max|sigma| {np.abs(so).max():.3f}, max|d sigma| {err:.2e}")
     assert err < 1e-9 * max(1.0, np.abs(so).max()), err
+
+
+def test_gpu_eri_blocks_vs_mpmath_mcmurchie_davidson(drv):
+    """oqpb_eri_block (the CUDA shellquartet) against the independent 40-digit McMurchie-Davidson evaluation of
+    tests/md_eri.py: d / f quartets on up to four centres, no oracle in between."""
+    import md_eri
+    bs = B.BasisSet(B.water_dimer(), "cc-pvtz", spherical=False)
+    drv.init(bs)
+    drv.set_screening()
+    worst = 0.0
+    for q in [(9, 15, 31, 21), (9, 9, 15, 13), (15, 21, 7, 13), (31, 26, 21, 16)]:
+        ref = np.array(md_eri.shell_quartet(bs, *q))
+        blk = drv.eri_block(*q)
+        assert blk.shape == ref.shape
+        err = np.abs(blk - ref).max() / np.abs(ref).max()
+        worst = max(worst, err)
+        assert err < 1e-12, (q, err)
+    print(f"GPU vs McMurchie-Davidson/mpmath: worst relative block error {worst:.1e}")

@@ -297,3 +297,34 @@ def test_mrsf_ch2o_golden(oracle_mod):
     w = np.linalg.eigvalsh(A)
     assert np.allclose(w[:4], g["roots_nstate20"], atol=2e-8), (w[:4], g["roots_nstate20"])
     assert np.allclose(w[:3], g["td_energies"], atol=5e-7), (w[:3], g["td_energies"])
+
+
+MD_QUARTETS = [(9, 15, 31, 21), (9, 8, 31, 30), (9, 9, 15, 13), (15, 21, 7, 13), (31, 26, 21, 16), (7, 0, 26, 22), (8, 4, 30, 43)]
+
+
+def test_oracle_eri_vs_mpmath_mcmurchie_davidson(oracle_mod):
+    """SURVEY 8c cross-check: d / f shell quartets of (H2O)2 / cc-pVTZ (Cartesian 6d/10f, up to four distinct centres,
+    contracted s / p partners) from an independent 40-digit McMurchie-Davidson evaluation (tests/md_eri.py: Hermite
+    expansion + Boys function, no Rys quadrature anywhere) against shellquartet of the oracle.  Pins the f-shell and d-shell
+    integral values, their normalisation (normalize_ints, int2.F90:1187-1207) and the reference's component order without
+    the real binary; the Cartesian -> pure tables are pinned separately against the reference's own (test above)."""
+    import md_eri
+    bs = B.BasisSet(B.water_dimer(), "cc-pvtz", spherical=False)
+    o = oracle_mod.Oracle(bs)
+    o.set_screening()
+    worst = 0.0
+    for q in MD_QUARTETS:
+        ref = np.array(md_eri.shell_quartet(bs, *q))
+        i, j, k, l = q
+        blk = o.eri_block(max(i, j), min(i, j), max(k, l), min(k, l))  # shellquartet takes canonical shell order
+        if i < j:
+            blk = blk.transpose(1, 0, 2, 3)
+        if k < l:
+            blk = blk.transpose(0, 1, 3, 2)
+        assert blk.shape == ref.shape
+        scale = np.abs(ref).max()
+        assert scale > 1e-6, (q, scale)  # far above the primitive-pair cutoffs (int2_pairs.F90:245-249), which drop ~1e-10 terms
+        err = np.abs(blk - ref).max() / scale
+        worst = max(worst, err)
+        assert err < 1e-12, (q, [int(bs.am[s]) for s in q], err)
+    print(f"oracle vs McMurchie-Davidson/mpmath: {len(MD_QUARTETS)} quartets, worst relative block error {worst:.1e}")
