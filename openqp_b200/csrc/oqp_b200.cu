@@ -355,13 +355,14 @@ __global__ void k_entry_screen(long nent, const PairEntry* __restrict__ ent, con
 // buffer in ket-list order: a warp of the ERI kernels then sees runs of quartets with the same bra and the same
 // ket shell c.
 constexpr int ENUM_NT = 256;
+constexpr int ENUM_BITS_MAX = 1 << 17;  // kets per bra whose test outcomes are kept as bits in shared memory (16 KB)
 __global__ void __launch_bounds__(ENUM_NT)
 k_enum(const PairEntry* __restrict__ bra, const PairEntry* __restrict__ ket, const double* __restrict__ Qb,
        const double* __restrict__ Qk, const double* __restrict__ d4b, const double* __restrict__ d4k,
        const int* __restrict__ okb, const int* __restrict__ okk, const int* __restrict__ canb,
        const int* __restrict__ cank, const int* __restrict__ kmax, int p0, int p1, int pstride, int diag,
        const double* __restrict__ dsh, int nshell, double cutoff, int2* __restrict__ tasks, unsigned* __restrict__ count,
-       unsigned cap, int use_smem, int2* __restrict__ items, unsigned* __restrict__ nitems, unsigned item_cap) {
+       unsigned cap, int use_smem, int2* __restrict__ items, unsigned* __restrict__ nitems, unsigned item_cap, int bits_cap) {
   extern __shared__ double rows[];
   __shared__ unsigned s_w[ENUM_NT / 32];
   __shared__ unsigned s_base, s_ibase;
@@ -392,9 +393,18 @@ k_enum(const PairEntry* __restrict__ bra, const PairEntry* __restrict__ ket, con
     return bra_ok && !(res < cutoff);
   };
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  // pass 1: count
+  // pass 1: count; the outcome of every test is kept as one bit (one word per 32 consecutive kets) so that pass 2 does not
+  // load the ket entries, bounds and density rows a second time
+  unsigned* bits = reinterpret_cast<unsigned*>(rows + (use_smem ? 2 * nshell : 0));
+  const bool keep_bits = nk <= bits_cap;
   unsigned cnt = 0;
-  for (int q = threadIdx.x; q < nk; q += ENUM_NT) cnt += test(q) ? 1u : 0u;
+  for (int q0 = 0; q0 < nk; q0 += ENUM_NT) {
+    const int q = q0 + threadIdx.x;
+    const bool sv = q < nk && test(q);
+    const unsigned m = __ballot_sync(0xffffffffu, sv);
+    if (keep_bits && lane == 0 && q < nk) bits[q >> 5] = m;  // (lane 0 holds the first ket of the warp's 32)
+    cnt += sv ? 1u : 0u;
+  }
   cnt = __reduce_add_sync(0xffffffffu, cnt);
   if (lane == 0) s_w[w] = cnt;
   __syncthreads();
@@ -421,8 +431,15 @@ k_enum(const PairEntry* __restrict__ bra, const PairEntry* __restrict__ ket, con
   // pass 2: write in ket-list order
   for (int q0 = 0; q0 < nk; q0 += ENUM_NT) {
     const int q = q0 + threadIdx.x;
-    const bool surv = q < nk && test(q);
-    const unsigned mask = __ballot_sync(0xffffffffu, surv);
+    unsigned mask;
+    bool surv;
+    if (keep_bits) {
+      mask = (q0 + (w << 5)) < nk ? bits[(q0 >> 5) + w] : 0u;
+      surv = (mask >> lane) & 1u;
+    } else {
+      surv = q < nk && test(q);
+      mask = __ballot_sync(0xffffffffu, surv);
+    }
     if (lane == 0) s_w[w] = __popc(mask);
     __syncthreads();
     unsigned off = 0, tot = 0;
@@ -989,10 +1006,11 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   std::vector<int2> rec_tmp;
   std::vector<float> chunk_ms;
   const size_t smem_rows = (size_t)2 * ns * sizeof(double);
-  const int use_smem = smem_rows <= 96 * 1024;
+  const int use_smem = smem_rows <= 80 * 1024;
+  const size_t smem_enum_max = (use_smem ? smem_rows : 0) + ENUM_BITS_MAX / 8;  // density rows + one bit per candidate ket
   static DevFlags enum_flags;  // per device
   bool& enum_attr = enum_flags.cur();
-  if (use_smem && smem_rows > 48 * 1024 && !enum_attr) {
+  if (smem_enum_max > 48 * 1024 && !enum_attr) {
     CK(cudaFuncSetAttribute(k_enum, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     enum_attr = true;
   }
@@ -1020,13 +1038,14 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     int nbra = (ch.p1 - ch.p0 + ch.nr - 1) / ch.nr + 1;
     // first bra of this rank at or after p0
     int pstart = ch.p0 + ((ch.rk - ch.p0 % ch.nr) % ch.nr + ch.nr) % ch.nr;
-    k_enum<<<nbra, ENUM_NT, use_smem ? smem_rows : 0, cs>>>(
+    const int bits_cap = std::min(((T.cls_off[ch.pcb + 1] - T.cls_off[ch.pcb]) + 31) & ~31, ENUM_BITS_MAX);
+    k_enum<<<nbra, ENUM_NT, (use_smem ? smem_rows : 0) + (size_t)bits_cap / 8, cs>>>(
         T.d_ent.as<PairEntry>() + offa, T.d_ent.as<PairEntry>() + offb, dQ + offa,
         dQ + offb, ctx->d_d4.as<double>() + offa, ctx->d_d4.as<double>() + offb,
         ctx->d_ok.as<int>() + offa, ctx->d_ok.as<int>() + offb, T.d_canon.as<int>() + offa,
         T.d_canon.as<int>() + offb, d_km.as<int>() + km_off[ci], pstart, ch.p1, ch.nr, ch.pca == ch.pcb,
         ctx->d_dsh.as<double>(), ns, cutoff, d_tasks, d_cnt + 4 * c, (unsigned)ctx->task_cap, use_smem, d_items,
-        d_cnt + 4 * c + 2, (unsigned)item_cap);
+        d_cnt + 4 * c + 2, (unsigned)item_cap, bits_cap);
     CK(cudaGetLastError());
     EriArgs A;
     fill_common_args(ctx, T, ch.pca, ch.pcb, A);
