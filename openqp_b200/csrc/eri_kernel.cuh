@@ -59,6 +59,18 @@
 #ifndef OQPB_RUN_M
 #define OQPB_RUN_M 7
 #endif
+#ifndef OQPB_ROOT_UNROLL
+#define OQPB_ROOT_UNROLL 2
+#endif
+#ifndef OQPB_ROOT_UNROLL_MAX
+#define OQPB_ROOT_UNROLL_MAX 18
+#endif
+#ifndef OQPB_KP_UNROLL
+#define OQPB_KP_UNROLL 1
+#endif
+#ifndef OQPB_KP_UNROLL_MAXR
+#define OQPB_KP_UNROLL_MAXR 1
+#endif
 #ifndef OQPB_MED_VOLATILE
 #define OQPB_MED_VOLATILE 0
 #endif
@@ -70,6 +82,8 @@
 #endif
 
 namespace oqpb {
+__host__ __device__ constexpr int root_unroll() { return OQPB_ROOT_UNROLL; }
+__host__ __device__ constexpr int root_unroll_max() { return OQPB_ROOT_UNROLL_MAX; }
 
 struct alignas(16) PairEntry {
   int sa, sb;      // shells, am(sa) >= am(sb); equal am: sa is the canonical row shell (sa >= sb)
@@ -1519,6 +1533,8 @@ __device__ __forceinline__ void eval_quartet_thread(const EriArgs& A, const Pair
     if ((da0 * db) * (da0 * db) < thr) break;
     double2 np01 = make_double2(0, 0), np23 = np01, np45 = np01;
     if (PIPE && pb.pcnt > 0) { np01 = __ldg(pp0); np23 = __ldg(pp0 + 1); np45 = __ldg(pp0 + 2); }
+    constexpr int KP_UNROLL = (R <= OQPB_KP_UNROLL_MAXR && !WPQ) ? OQPB_KP_UNROLL : 1;
+#pragma unroll KP_UNROLL
     for (int kp = kp0; kp < pb.pcnt; kp += kps) {
       double2 p01 = np01, p23 = np23, p45 = np45;
       if constexpr (PIPE) {
@@ -1549,7 +1565,11 @@ __device__ __forceinline__ void eval_quartet_thread(const EriArgs& A, const Pair
       const double pref = pfac * rsab;
       const double rz = rho * zinv, re = rho * einv, hz = 0.5 * zinv, he = 0.5 * einv;
       const RysX rx = rys_prepare<R>(A, X);
-#pragma unroll 1
+      // OQPB_ROOT_UNROLL > 1: the register classes unroll the root loop so that the next root's interpolation chain overlaps
+      // the recurrences of the current one (the thread-per-quartet kernels are latency bound at 8-16 warps per SM)
+      // measured on (H2O)32: -3...-8 % on (ps|ps), (ds|ss), (pp|ss), (dp|ss), (fs|ss), (pp|ps); neutral or slower above
+      constexpr int ROOT_UNROLL = (GS || R == 1 || (NCART4 > root_unroll_max() && !(LA == 1 && LB == 1 && LC == 1 && LD == 0))) ? 1 : root_unroll();
+#pragma unroll ROOT_UNROLL
       for (int r = 0; r < R; ++r) {
         double t2, w;
         rys_pair<R, RSM>(A, gsm, rx, r, t2, w);
