@@ -71,6 +71,9 @@
 #ifndef OQPB_KP_UNROLL_MAXR
 #define OQPB_KP_UNROLL_MAXR 1
 #endif
+#ifndef OQPB_GRP_STATIC_WALK
+#define OQPB_GRP_STATIC_WALK 0
+#endif
 #ifndef OQPB_MED_VOLATILE
 #define OQPB_MED_VOLATILE 0
 #endif
@@ -2086,11 +2089,17 @@ eri_group_kernel(const EriArgs A) {
   const unsigned ntasks = A.task_cap ? min(*A.ntasks, A.task_cap) : *A.ntasks;
   unsigned long long st_prim = 0, st_ints = 0;
 
+#if OQPB_GRP_STATIC_WALK
+  // static warp-strided walk over the task list (helped the ket-owner kernel; here measured 1.5-2.5 % SLOWER than the dynamic
+  // fetch: the contracted quartets of this kernel's classes vary more in cost)
+  for (unsigned base = (blockIdx.x * GC::WPC + w) * QPW; base < ntasks; base += gridDim.x * GC::WPC * QPW) {
+#else
   for (;;) {
     unsigned base = 0;
     if (lane == 0) base = atomicAdd(A.counter, (unsigned)QPW);
     base = __shfl_sync(FULL, base, 0);
     if (base >= ntasks) break;
+#endif
     __syncwarp();
     if (t == 0) {
       unsigned ti = base + g;
