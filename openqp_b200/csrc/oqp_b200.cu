@@ -172,6 +172,13 @@ struct oqpb_ctx {
   int nlanes = 4;      // OQPB_NLANES
   int grid_pct = 100;  // OQPB_GRID_PCT: scales the per-class grid caps
   bool use_run = true;   // OQPB_RUN=0: task kernels only
+  bool use_graph = false;            // OQPB_GRAPH=1: replay the launch section as a CUDA graph (measured neutral, see run_build)
+  size_t graph_max_chunks = 600;     // OQPB_GRAPH_MAX: builds with more chunks are launched eagerly (launch latency is hidden there)
+  struct GraphSlot {
+    std::string key;
+    cudaGraphExec_t exec = nullptr;
+    void reset() { if (exec) cudaGraphExecDestroy(exec); exec = nullptr; key.clear(); }
+  } graph[2];                        // regular / attenuated plan
   double whole_ms = 2.5;   // OQPB_WHOLE_MS: a list pair is shared by round(estimated ms / whole_ms) ranks (0 = always by all ranks)
   int use_kown = 1;      // OQPB_KOWN: 0 = never the ket-owner group kernel, 1 = the classes it wins (default), 2 = every class it covers
   int run_max_bucket_sum = 2;  // OQPB_RUN_BUCKETS
@@ -846,6 +853,7 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   // ---- plan (cached, see BuildPlan): per list pair, kmax[p] by binary search over the suffix maxima of the ket
   // list's Schwarz bounds; chunk boundaries
   using Chunk = PlanChunk;
+  using GraphSlot = oqpb_ctx::GraphSlot;
   const int nr = ctx->nranks, rk = ctx->rank;
   double bound4p = bound4;
   if (bound4 > 0) { int e; std::frexp(bound4, &e); bound4p = std::ldexp(1.0, e); }  // next power of two >= bound4
@@ -985,7 +993,6 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   size_t nch = chunks.size();
   if ((rc = ensure_counts(ctx, 4 * nch + 4))) return rc;
   CK(ctx->d_counters.ensure((4 * nch + 4) * sizeof(unsigned)));
-  CK(cudaMemsetAsync(ctx->d_counters.p, 0, (4 * nch + 4) * sizeof(unsigned), ctx->stream));
   unsigned* d_cnt = ctx->d_counters.as<unsigned>();  // [4*c] = ntasks, [4*c+1] = fetch counter, [4*c+2] = run items
   const int nlane = ctx->profile || ctx->record ? 1 : ctx->nlanes;
   // run kernels (one Fock matrix, SYM consumers): warp items = pieces of RUN_LEN kets, at most one short piece per bra
@@ -998,7 +1005,6 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     if (run_ok) CK(ctx->d_items[l].ensure(item_cap * sizeof(int2)));
   }
   CK(ctx->d_stats.ensure((2 * nch + 2) * sizeof(unsigned long long)));
-  CK(cudaMemsetAsync(ctx->d_stats.p, 0, (2 * nch + 2) * sizeof(unsigned long long), ctx->stream));
   std::vector<unsigned long long> h_stats(2 * nch + 2, 0);
   const ClassEntry* tab = class_table(ctx->pure_l[2] | (ctx->pure_l[3] << 1));
   ctx->rec.clear();
@@ -1014,7 +1020,11 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     CK(cudaFuncSetAttribute(k_enum, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     enum_attr = true;
   }
-  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  // ---- the launch section of a build: counters cleared, then per chunk one enumeration and one ERI launch, on nlane
+  // streams forked from / joined into ctx->stream.  Run eagerly, or captured into a CUDA graph and replayed (below).
+  auto launch_all = [&]() -> int {
+  CK(cudaMemsetAsync(ctx->d_counters.p, 0, (4 * nch + 4) * sizeof(unsigned), ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_stats.p, 0, (2 * nch + 2) * sizeof(unsigned long long), ctx->stream));
   if (nlane > 1) {
     CK(cudaEventRecord(ctx->fork_ev, ctx->stream));
     for (int l = 0; l < nlane; ++l) CK(cudaStreamWaitEvent(ctx->lane[l], ctx->fork_ev, 0));
@@ -1104,6 +1114,57 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
     for (int l = 0; l < nlane; ++l) {
       CK(cudaEventRecord(ctx->lane_ev[l], ctx->lane[l]));
       CK(cudaStreamWaitEvent(ctx->stream, ctx->lane_ev[l], 0));
+    }
+  }
+  return OQPB_OK;
+  };
+  // Optional CUDA-graph replay of the cached plan (OQPB_GRAPH=1).  The key holds everything the kernel arguments are made
+  // of; the first build with a new key runs eagerly (it also performs the one-time cudaFuncSetAttribute calls), the second
+  // is captured, later ones are one cudaGraphLaunch.  Measured NEUTRAL on every configuration (c1 1.40 vs 1.41 ms, c2 6.90
+  // vs 6.86, c3 19.2 vs 19.3): the small molecules are not bound by the host's launch rate but by the serial depth of the
+  // ~30 dependent enumerate -> evaluate pairs per stream lane, ~40 us each (a few heavily contracted quartets per launch);
+  // hence off by default.
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  {
+    GraphSlot& G = ctx->graph[S.attenuated ? 1 : 0];
+    const bool graph_ok = ctx->use_graph && !ctx->profile && !ctx->record && nch > 0 && nch <= ctx->graph_max_chunks;
+    std::string key;
+    if (graph_ok) {
+      auto put = [&](const void* p_, size_t n_) { key.append(reinterpret_cast<const char*>(p_), n_); };
+#define KPUT(x) do { auto v_ = (x); put(&v_, sizeof v_); } while (0)
+      KPUT(P.gen); KPUT(P.bound4); KPUT(nch); KPUT(S.mode); KPUT(S.nmat); KPUT(S.cj); KPUT(S.ck); KPUT(S.Pgen); KPUT(S.Fgen);
+      KPUT(S.gen_nm); KPUT(S.gen_ncoul); KPUT(S.gen_nvec); KPUT(S.gen_mcount); KPUT(S.gen_xoff); KPUT(S.attenuated);
+      for (int m = 0; m < S.nmat; ++m) { KPUT(S.DJ[m]); KPUT(S.DK[m]); KPUT(S.F[m]); }
+      KPUT(cutoff); KPUT(ctx->cut.pair); KPUT(T.att_mu); KPUT(ctx->task_cap); KPUT(nlane); KPUT(ctx->use_kown); KPUT(run_ok);
+      KPUT(ctx->run_max_bucket_sum); KPUT(ctx->wpq_max_tasks); KPUT(ctx->grid_pct); KPUT(ctx->d_counters.p); KPUT(ctx->d_stats.p);
+      KPUT(ctx->d_dsh.p); KPUT(ctx->d_d4.p); KPUT(ctx->d_ok.p); KPUT(d_km.p); KPUT(T.d_ent.p); KPUT(dQ); KPUT(T.d_canon.p);
+      for (int l = 0; l < nlane; ++l) { KPUT(ctx->d_tasks[l].p); KPUT(ctx->d_items[l].p); }
+#undef KPUT
+    }
+    if (graph_ok && G.exec && G.key == key) {
+      CK(cudaGraphLaunch(G.exec, ctx->stream));
+      ctx->st_launches = 2 * (long long)nch;
+    } else if (graph_ok && !G.exec && G.key == key) {
+      bool captured = false;
+      if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const int lrc = launch_all();
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce_ = cudaStreamEndCapture(ctx->stream, &graph);
+        if (lrc == OQPB_OK && ce_ == cudaSuccess && graph && cudaGraphInstantiate(&G.exec, graph, 0) == cudaSuccess) captured = true;
+        if (graph) cudaGraphDestroy(graph);
+      }
+      if (captured) {
+        CK(cudaGraphLaunch(G.exec, ctx->stream));
+      } else {  // capture not possible here: no graphs for this context, run eagerly
+        cudaGetLastError();
+        G.reset();
+        ctx->use_graph = false;
+        ctx->st_launches = 0;
+        if ((rc = launch_all())) return rc;
+      }
+    } else {
+      if (graph_ok) { G.reset(); G.key = key; }
+      if ((rc = launch_all())) return rc;
     }
   }
   const double t_launched = tnow();
@@ -1264,6 +1325,8 @@ int oqpb_ctx_create(oqpb_ctx** out, int device) {
   if (const char* e = getenv("OQPB_RUN")) ctx->use_run = atoi(e) != 0;
   if (const char* e = getenv("OQPB_KOWN")) ctx->use_kown = atoi(e);
   if (const char* e = getenv("OQPB_WHOLE_MS")) ctx->whole_ms = atof(e);
+  if (const char* e = getenv("OQPB_GRAPH")) ctx->use_graph = atoi(e) != 0;
+  if (const char* e = getenv("OQPB_GRAPH_MAX")) ctx->graph_max_chunks = (size_t)std::max(0, atoi(e));
   if (const char* e = getenv("OQPB_RUN_BUCKETS")) ctx->run_max_bucket_sum = atoi(e);
   if (const char* e = getenv("OQPB_WPQ_MAX")) ctx->wpq_max_tasks = (size_t)std::max(0, atoi(e));
   if (const char* e = getenv("OQPB_TASK_CAP_LOG2")) ctx->task_cap = (size_t)1 << std::max(16, std::min(28, atoi(e)));
@@ -1333,6 +1396,7 @@ void oqpb_ctx_destroy(oqpb_ctx* ctx) {
                     &ctx->d_d4, &ctx->d_rowsbuf, &ctx->plan[0].d_km, &ctx->plan[1].d_km, &ctx->d_counters, &ctx->d_Dsq, &ctx->d_F, &ctx->d_Din,
                     &ctx->d_stats, &ctx->d_gen_in, &ctx->d_gen_out, &ctx->d_mask})
     b->release();
+  ctx->graph[0].reset(); ctx->graph[1].reset();
   for (int l = 0; l < oqpb_ctx::NSTREAM; ++l) { ctx->d_tasks[l].release(); ctx->d_items[l].release(); }
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
   cudaEventDestroy(ctx->ev0);
