@@ -13,14 +13,19 @@
 //     The bra-owner group kernel re-reads the block from shared memory six times and loads a density element per FMA.
 // Phases per primitive quartet as in eri_group_kernel (roots, (root, direction) recurrences in registers, assembly).
 #ifndef OQPB_KOWN_ACC
-#define OQPB_KOWN_ACC 20
+#define OQPB_KOWN_ACC 60
 #endif
 #ifndef OQPB_KOWN_REGS
 #define OQPB_KOWN_REGS 128
 #endif
 // per-class override of the ket components per lane (0 = heuristic)
+// Measured on (H2O)32 (gpurun_out/s8, s21): one ket component per lane wins wherever the lane then holds <= 40 accumulators;
+// the (fp| bra (30 components) takes two ket components per lane and the (fd| bra (60) one, both WITHOUT a register cap
+// (168 registers cost (fd|ps) 40 %: 600-1600 bytes of spills).
 template <int LA, int LB, int LC, int LD>
-__host__ __device__ constexpr int kown_kpl_override() { return 0; }
+__host__ __device__ constexpr int kown_kpl_override() {
+  return (LA == 3 && LB == 1) ? 0 : ((LA == 3 && LB == 2) ? 1 : 1);
+}
 
 template <int LA, int LB, int LC, int LD, int PV>
 struct KownCfg {
@@ -77,7 +82,15 @@ struct KownCfg {
   static constexpr int NT = 32 * WPC;
   static constexpr size_t SMEM = (size_t)WPC * QPW * QBYTES;
   // register cap requested from ptxas
-  static constexpr int REGCAP = KPL * NBRA <= 40 ? OQPB_KOWN_REGS : (KPL * NBRA <= 60 ? 168 : 255);
+#ifndef OQPB_KOWN_REGS_MID
+#define OQPB_KOWN_REGS_MID 255
+#endif
+#ifndef OQPB_KOWN_REGS_36
+#define OQPB_KOWN_REGS_36 168
+#endif
+  // register cap by accumulators per lane (measured per class on (H2O)32): <= 20 -> 128 ((dp| bra: 168 is 9 % slower),
+  // 21..40 -> 168 ((dd| bra: (dd|ds) 32.7 -> 22.0 ms, (dd|pp) 23.3 -> 15.9 ms against 128), above -> no cap
+  static constexpr int REGCAP = KPL * NBRA <= 20 ? OQPB_KOWN_REGS : (KPL * NBRA <= 40 ? OQPB_KOWN_REGS_36 : (KPL * NBRA <= 60 ? OQPB_KOWN_REGS_MID : 255));
 };
 
 // segmented sums over the quartet slots of a warp for any group size (QPW not a power of two)

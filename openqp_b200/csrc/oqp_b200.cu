@@ -169,7 +169,7 @@ struct oqpb_ctx {
   DevBuf d_tasks[NSTREAM], d_items[NSTREAM], d_counters, d_Dsq, d_F, d_Din, d_stats, d_gen_in, d_gen_out;
   cudaStream_t lane[NSTREAM] = {};
   cudaEvent_t lane_ev[NSTREAM] = {};
-  int nlanes = 4;      // OQPB_NLANES
+  int nlanes = 0;      // OQPB_NLANES (0 = by build size: 4 or 8, see run_build)
   int grid_pct = 100;  // OQPB_GRID_PCT: scales the per-class grid caps
   bool use_run = true;   // OQPB_RUN=0: task kernels only
   bool use_graph = false;            // OQPB_GRAPH=1: replay the launch section as a CUDA graph (measured neutral, see run_build)
@@ -994,7 +994,12 @@ int run_build(oqpb_ctx* ctx, const BuildSpec& S) {
   if ((rc = ensure_counts(ctx, 4 * nch + 4))) return rc;
   CK(ctx->d_counters.ensure((4 * nch + 4) * sizeof(unsigned)));
   unsigned* d_cnt = ctx->d_counters.as<unsigned>();  // [4*c] = ntasks, [4*c+1] = fetch counter, [4*c+2] = run items
-  const int nlane = ctx->profile || ctx->record ? 1 : ctx->nlanes;
+  // stream lanes: 4 by default; 8 for builds of 1e5 .. 1e8 candidate quartets (benzene/cc-pVDZ -18 %, n-C20H42 -1 %: their
+  // device time is the serial depth of dependent enumerate -> evaluate pairs per lane), measured neutral on (H2O)32 and
+  // 12 % slower on the 1.6e3 quartets of H2O/6-31G(d)
+  size_t cand_total = 0;
+  for (const Chunk& ch : chunks) cand_total += ch.cand;
+  const int nlane = ctx->profile || ctx->record ? 1 : (ctx->nlanes > 0 ? ctx->nlanes : (cand_total >= 100000 && cand_total < 100000000 ? 8 : 4));
   // run kernels (one Fock matrix, SYM consumers): warp items = pieces of RUN_LEN kets, at most one short piece per bra
   const bool run_ok = ctx->use_run && S.mode == MODE_SYM && S.nmat == 1 && !ctx->record;
   size_t max_list = 0;

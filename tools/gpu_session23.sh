@@ -1,0 +1,6 @@
+#!/bin/bash
+tag=${1:-s23}
+mkdir -p gpurun_out
+timeout 600 python tools/class_profile.py w32 > gpurun_out/${tag}_class_w32_def.txt 2>&1; head -1 gpurun_out/${tag}_class_w32_def.txt
+OQPB_KOWN=2 timeout 600 python tools/class_profile.py w32 > gpurun_out/${tag}_class_w32_k2.txt 2>&1; head -1 gpurun_out/${tag}_class_w32_k2.txt
+OQPB_KOWN=2 OQPB_LIB=openqp_b200/libopenqp_b200_m255.so timeout 600 python tools/class_profile.py w32 > gpurun_out/${tag}_class_w32_k2m255.txt 2>&1; head -1 gpurun_out/${tag}_class_w32_k2m255.txt
