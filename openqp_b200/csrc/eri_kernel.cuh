@@ -2566,7 +2566,7 @@ constexpr bool class_kown_default() {
   // per-class A/B against the bra-owner group kernel / the thread-per-quartet kernels (gpurun_out/s8_class_w32_*.txt):
   // the classes with >= 160 Cartesian integrals and a ket of p or d shells win 12-60 %
   return key == 2111 || key == 2220 || key == 2221 || key == 3121 || key == 3131 || key == 3221 || key == 3220 || key == 3211 ||
-         key == 3231 || key == 3210 || key == 3111 || key == 3120 || key == 3230 || key == 3130 || key == 2211;
+         key == 3231 || key == 3210 || key == 3111 || key == 3120 || key == 3230 || key == 3130 || key == 2211 || key == 2121;
 }
 
 template <int LA, int LB, int LC, int LD>
