@@ -81,7 +81,10 @@ struct KownCfg {
   static constexpr int QSM0 = RWOFF + RW;
   static constexpr int QSM = (QSM0 / 2) % 2 == 1 ? QSM0 : QSM0 + 2;  // per-quartet stride (doubles), QSM/2 odd
   static constexpr int QBYTES = QSM * 8 + 32;
-  static constexpr int WPC = (4 * QPW * QBYTES <= 48 * 1024) ? 4 : ((2 * QPW * QBYTES <= 64 * 1024) ? 2 : 1);
+#ifndef OQPB_KOWN_WPC
+#define OQPB_KOWN_WPC 4
+#endif
+  static constexpr int WPC = (OQPB_KOWN_WPC >= 4 && 4 * QPW * QBYTES <= 48 * 1024) ? 4 : ((OQPB_KOWN_WPC >= 2 && 2 * QPW * QBYTES <= 64 * 1024) ? 2 : 1);
   static constexpr int NT = 32 * WPC;
   static constexpr size_t SMEM = (size_t)WPC * QPW * QBYTES;
   // register cap requested from ptxas
