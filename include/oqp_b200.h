@@ -70,10 +70,13 @@ int oqpb_set_screening(oqpb_ctx* ctx, const double* schwarz_in);
 int oqpb_get_schwarz(oqpb_ctx* ctx, double* schwarz_out /* nshell*nshell */);
 
 /* Multi-GPU / MPI replicated-data split of the work, the role of the reference's `mod(ij_pair, size) == rank`
- * (int2.F90:759-761): the bras of every pair list (angular-momentum class x contraction bucket, Schwarz-sorted) are
- * dealt cyclically, p % nranks == rank inside each list, so every rank gets the same class mix.  A rank's slice (and
- * its nskipped) therefore differs from the slice a native OpenQP rank would take: all ranks of a job must use this
- * library.  The caller sums the partial results (pe%allreduce, int2.F90:1396) -- or uses a multi-device context.     */
+ * (int2.F90:759-761).  Every pair list (angular-momentum class x contraction bucket, Schwarz-sorted) pair is shared by
+ * s = round(estimated ms / 2.5) of the ranks (1 <= s <= nranks, the least loaded ones by a per-class cost model that every
+ * rank evaluates identically) and the bras of the list are dealt cyclically among those, p % s == j: long list pairs are
+ * split over all ranks with the same class mix, short ones run as one launch on one rank instead of nranks tiny ones.  A
+ * rank's slice (and its nskipped) therefore differs from the slice a native OpenQP rank would take: all ranks of a job
+ * must use this library; the slices are disjoint and their nskipped add up to the single-rank value.  The caller sums
+ * the partial results (pe%allreduce, int2.F90:1396) -- or uses a multi-device context.                               */
 int oqpb_set_partition(oqpb_ctx* ctx, int rank, int nranks);
 
 /* Test hook: restrict the following builds to the quartets whose reference bra pair (the canonically larger
