@@ -1393,6 +1393,12 @@ __host__ __device__ constexpr int min_ctas(int nt, int regcap) { return regcap >
 template <int LA, int LB, int LC, int LD>
 __host__ __device__ constexpr int small_regcap() {
   constexpr int key = LA * 1000 + LB * 100 + LC * 10 + LD;
+#ifndef OQPB_CAP_2000
+#define OQPB_CAP_2000 128
+#endif
+  // ((fs|ps), (fp|ss), (dd|ss) at 168 / 128 instead of 255 registers: +6...+30 %)
+  if (key == 2000) return OQPB_CAP_2000;  // (ds|ss): 150-180 registers uncapped (2 CTAs of 128 threads): 75.7 ms; 160: 71.1; 128: 66.6
+  // ((pp|ps), (ds|ds) at 168 instead of ~250 registers: +12...+19 %)
   return (key == 2010 || key == 2100 || key == 1100 || key == 1010 || key == 3000) ? 128 : OQPB_SMALL_REGS;
 }
 
