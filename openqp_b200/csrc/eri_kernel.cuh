@@ -6,12 +6,17 @@
 //   (int2.F90:1187-1207, int_rys.F90:715-785) -> storeints (int2.F90:1741-1865) -> consumer update
 //   (int2.F90:1414-1578, tdhf_lib.F90:140-224, tdhf_mrsf_lib.F90:218-333).
 //
-// Three kernel families, chosen per class at compile time (launch_eri):
+// Kernel families, chosen per class at compile time (launch_eri*) and per launch by the host (run_build):
 //   eri_small_kernel   one thread = one quartet; classes with <= 36 Cartesian integrals keep everything in registers,
-//                      classes with <= 150 keep the gx/gy/gz tables of a root in shared memory ([entry][thread]);
-//   eri_group_kernel   a quartet is owned by an aligned group of G = 4..32 lanes of one warp (__syncwarp only): roots,
-//                      2-D VRR + HRR per (root, direction) in registers, tables in shared memory ([c][d][a][b]),
-//                      register-tiled assembly, block projected and digested from shared memory;
+//                      classes with <= 150 write the gx/gy/gz tables of a root to shared memory ([entry][thread]; ptxas
+//                      forwards the stored values, so they live in registers too); WPQ variant: one warp = one quartet;
+//   eri_run_kernel     the same evaluation, but a warp walks a run of consecutive surviving kets of ONE bra (bra entry and
+//                      D_ab loaded once, J_ab accumulated in registers over the run); SYM consumers with one Fock matrix;
+//   eri_group_kernel   a quartet is owned by an aligned group of G = 4..32 lanes of one warp (__syncwarp only), lanes own
+//                      BRA component pairs: roots, 2-D VRR + HRR per (root, direction) in registers, tables in shared
+//                      memory ([c][d][a][b]), register-tiled assembly, block projected and digested from shared memory;
+//   eri_kown_kernel    (eri_kown.cuh) groups of any size whose lanes own KET components with all bra components in
+//                      registers: table rows read once (LDS.128, broadcast), bra projection and SYM digestion from registers;
 //   eri_kernel         CTA teams (NA*NB*KS threads per quartet, CTA barriers) for the few largest classes.
 // Per primitive quartet:  roots/weights (Chebyshev tables) -> 2-D VRR on centres A and C -> HRR to B and D ->
 // I += gx*gy*gz.  Then the Cartesian block is normalised / projected to pure functions index by index (sparse
@@ -1542,6 +1547,8 @@ __device__ __forceinline__ void eval_quartet_thread(const EriArgs& A, const Pair
     if ((da0 * db) * (da0 * db) < thr) break;
     double2 np01 = make_double2(0, 0), np23 = np01, np45 = np01;
     if (PIPE && pb.pcnt > 0) { np01 = __ldg(pp0); np23 = __ldg(pp0 + 1); np45 = __ldg(pp0 + 2); }
+    // (two bra primitives per iteration evaluated branch-free side by side for the R = 1 classes: (ps|ss) 124 -> 157 ms,
+    // (ss|ss) 49 -> 56 ms -- the work spent on primitives that fail the tests outweighs the hidden latency)
     constexpr int KP_UNROLL = (R <= OQPB_KP_UNROLL_MAXR && !WPQ) ? OQPB_KP_UNROLL : 1;
 #pragma unroll KP_UNROLL
     for (int kp = kp0; kp < pb.pcnt; kp += kps) {

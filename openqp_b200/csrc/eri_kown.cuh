@@ -151,7 +151,7 @@ eri_kown_kernel(const EriArgs A) {
   constexpr int N0 = KC::N0, N1 = KC::N1, N2 = KC::N2, N3 = KC::N3, NTOT = N0 * N1 * N2 * N3, N01 = KC::N01, NKETP = KC::NKETP;
   constexpr int R = Cfg::R, NA = Cfg::NA, NB = Cfg::NB, NC = Cfg::NC, ND = Cfg::ND, NKET = Cfg::NKET, NBRA = KC::NBRA;
   constexpr int NMAX = Cfg::NMAX, MMAX = Cfg::MMAX, NKL1 = Cfg::NKL1, NIJ1 = Cfg::NIJ1;
-  constexpr int G = KC::G, KPL = KC::KPL, QPW = KC::QPW, ROW = KC::ROW, GSTR = KC::GSTR, QSM = KC::QSM, H = ROW / 2;
+  constexpr int G = KC::G, KPL = KC::KPL, QPW = KC::QPW, ROW = KC::ROW, GSTR = KC::GSTR, QSM = KC::QSM;
   constexpr unsigned FULL = 0xffffffffu;
 
   extern __shared__ double smem[];
@@ -352,7 +352,6 @@ eri_kown_kernel(const EriArgs A) {
       }
       __syncwarp();  // the tables are overwritten by the next primitive's B2, rw by its B1
     }
-    (void)H;
     // ---- bra indices normalised / projected in registers
     const bool work = valid && any;  // `any` is uniform over the group
     const double fac = (double)facf, cut = A.cutoff;
