@@ -170,7 +170,7 @@ struct oqpb_ctx {
   cudaStream_t lane[NSTREAM] = {};
   cudaEvent_t lane_ev[NSTREAM] = {};
   int nlanes = 0;      // OQPB_NLANES (0 = by build size: 4 or 8, see run_build)
-  int grid_pct = 100;  // OQPB_GRID_PCT: scales the per-class grid caps
+  int grid_pct = 50;   // OQPB_GRID_PCT: scales the per-class grid caps (100 -> 50 with 2^25 tasks per chunk: w32 1352 -> 1318 ms)
   bool use_run = true;   // OQPB_RUN=0: task kernels only
   bool use_graph = false;            // OQPB_GRAPH=1: replay the launch section as a CUDA graph (measured neutral, see run_build)
   size_t graph_max_chunks = 600;     // OQPB_GRAPH_MAX: builds with more chunks are launched eagerly (launch latency is hidden there)
@@ -184,7 +184,7 @@ struct oqpb_ctx {
   int run_max_bucket_sum = 2;  // OQPB_RUN_BUCKETS
   size_t wpq_max_tasks = 16384;  // OQPB_WPQ_MAX: largest launch (candidate quartets) that uses the warp-per-quartet kernels
   cudaEvent_t fork_ev = nullptr;
-  size_t task_cap = (size_t)1 << 23;
+  size_t task_cap = (size_t)1 << 25;  // quartets per chunk and stream lane (256 MB each); 2^23: +2.6 % launches/tails on w32
   int rank = 0, nranks = 1;
   // stats of the last build
   long long st_survivors = 0, st_skipped = 0, st_launches = 0;
