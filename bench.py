@@ -103,6 +103,26 @@ def workload_config(args, bs, W, sx, nvec=None):
     return cfg
 
 
+def dgemm_peak_tflops(dev, n=6144, reps=3):
+    """Independent cross-check of the FP64 roofline denominator: cuBLAS DGEMM through torch (informational; `roofline.peak`
+    stays the FMA microbenchmark of the library, which this number should not exceed by much).  None when it cannot run."""
+    try:
+        import torch
+        a = torch.randn(n, n, dtype=torch.float64, device=dev)
+        b = torch.randn(n, n, dtype=torch.float64, device=dev)
+        torch.matmul(a, b)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return 2.0 * n ** 3 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    except Exception:
+        return None
+
+
 def dram_traffic(workload):
     """HBM bytes per build summed over the ERI launches, from the committed ncu pass
     (profiles/r02_dram_<workload>.json, written by tools/dram_traffic.py on the GPU box); None when not captured."""
@@ -542,6 +562,7 @@ def main():
                                          "algorithmic bytes = 16 ntri + pair table, the bound is FP64",
                          "kernel": "eri_kernel<la,lb,lc,ld> family (Rys ERI + fused J/K digestion), per-GPU average",
                          "peak_source": "FP64 FMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                         "peak_cublas_dgemm_tflops": dgemm_peak_tflops(dev) if rank == 0 else None,
                          "algorithmic_flops_per_step": flops_all / args.steps, "kernel_ms_per_step": kernel_ms / args.steps,
                          "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peak_kind},
             "e2e": {"value": nq_step / (e2e_ms / args.steps * 1e-3), "unit": "quartets/s", "ms_per_step": e2e_ms / args.steps,
