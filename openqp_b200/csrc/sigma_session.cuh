@@ -165,7 +165,8 @@ int sig_apply_dev(SigSession& s, int nv) {
   const double* fa = s.fa.as<double>();
   const double* fb = s.fb.as<double>();
   const double* X = s.X.as<double>();
-  const double* Xp = X - (long)nb * na;  // X_v(i, j) = Xp[i + na j + ntrial v]   (iatogen, tdhf_lib.F90:480-498)
+  // X_v(i, j) = X[xo(i, j) + ntrial v], j >= nb   (iatogen, tdhf_lib.F90:480-498)
+  auto xo = [na, nb](int i, int j) { return (long)i + (long)na * (j - nb); };
   CK(s.d3.ensure((size_t)n2 * NM * sizeof(double)));
   CK(s.f3.ensure((size_t)n2 * NM * sizeof(double)));
   CK(s.TV.ensure((size_t)2 * nv * n * sizeof(double)));
@@ -188,12 +189,12 @@ int sig_apply_dev(SigSession& s, int nv) {
   const long cI = NM, cJ = (long)n * NM;  // strides of mu, nu inside a component
   auto comp = [&](int c) { return d3 + (long)c * nv; };
   // tv_w(mu) = sum_a C^b(mu, a) X(O_w, a), a virtual                     (:1001-1004, 1028-1031)
-  SG(n, 1, nvir, nv, 1.0, vb + (long)na * n, 1, n, 0, Xp + lr2 + (long)na * na, na, 0, ntrial, 0.0, tv2, 1, 0, n);
-  SG(n, 1, nvir, nv, 1.0, vb + (long)na * n, 1, n, 0, Xp + lr1 + (long)na * na, na, 0, ntrial, 0.0, tv1, 1, 0, n);
+  SG(n, 1, nvir, nv, 1.0, vb + (long)na * n, 1, n, 0, X + xo(lr2, na), na, 0, ntrial, 0.0, tv2, 1, 0, n);
+  SG(n, 1, nvir, nv, 1.0, vb + (long)na * n, 1, n, 0, X + xo(lr1, na), na, 0, ntrial, 0.0, tv1, 1, 0, n);
   if (nb > 0) {
     // tc_w(mu) = sum_i C^a(mu, i) X(i, O_w), i doubly occupied           (:1061-1064, 1088-1091)
-    SG(n, 1, nb, nv, 1.0, va, 1, n, 0, Xp + (long)na * lr1, 1, 0, ntrial, 0.0, tc1, 1, 0, n);
-    SG(n, 1, nb, nv, 1.0, va, 1, n, 0, Xp + (long)na * lr2, 1, 0, ntrial, 0.0, tc2, 1, 0, n);
+    SG(n, 1, nb, nv, 1.0, va, 1, n, 0, X + xo(0, lr1), 1, 0, ntrial, 0.0, tc1, 1, 0, n);
+    SG(n, 1, nb, nv, 1.0, va, 1, n, 0, X + xo(0, lr2), 1, 0, ntrial, 0.0, tc2, 1, 0, n);
   }
   // rank-1 updates: C(mu, nu) += alpha a(mu) b(nu)
   auto outer = [&](double* C, double alpha, const double* a, long sAb, const double* b, long sBb, const double* ab = nullptr,
@@ -211,14 +212,14 @@ int sig_apply_dev(SigSession& s, int nv) {
     if ((rc = outer(comp(5), 1.0, vb + (long)n * lr2, 0, tc1, n))) return rc;                           // co12  (:1141-1161)
     if ((rc = outer(comp(5), -1.0, vb + (long)n * lr1, 0, tc2, n))) return rc;
     // ball += C^a_c (X_cv C^b_v^T):  CV_v(nu, i) = sum_a C^b(nu, a) X(i, a);  ball(mu, nu) += sum_i C^a(mu, i) CV_v(nu, i)   (:1167-1175)
-    SG(n, nb, nvir, nv, 1.0, vb + (long)na * n, 1, n, 0, Xp + (long)na * na, na, 1, ntrial, 0.0, CV, 1, n, (long)n * nb);
+    SG(n, nb, nvir, nv, 1.0, vb + (long)na * n, 1, n, 0, X + xo(0, na), na, 1, ntrial, 0.0, CV, 1, n, (long)n * nb);
     SG(n, n, nb, nv, 1.0, va, 1, n, 0, CV, n, 1, (long)n * nb, 1.0, comp(6), cI, cJ, 1);
   }
   const double isq2 = 0.70710678118654752440;
-  const double* x11 = Xp + lr1 + (long)na * lr1;  // X_v(O1, O1), stride ntrial over v
+  const double* x11 = X + xo(lr1, lr1);  // X_v(O1, O1), stride ntrial over v
   if (kind == 1) {  // :1178-1186
-    if ((rc = outer(comp(6), 1.0, va + (long)n * lr2, 0, vb + (long)n * lr1, 0, Xp + lr2 + (long)na * lr1, ntrial))) return rc;
-    if ((rc = outer(comp(6), 1.0, va + (long)n * lr1, 0, vb + (long)n * lr2, 0, Xp + lr1 + (long)na * lr2, ntrial))) return rc;
+    if ((rc = outer(comp(6), 1.0, va + (long)n * lr2, 0, vb + (long)n * lr1, 0, X + xo(lr2, lr1), ntrial))) return rc;
+    if ((rc = outer(comp(6), 1.0, va + (long)n * lr1, 0, vb + (long)n * lr2, 0, X + xo(lr1, lr2), ntrial))) return rc;
     if ((rc = outer(comp(6), isq2, va + (long)n * lr1, 0, vb + (long)n * lr1, 0, x11, ntrial))) return rc;
     if ((rc = outer(comp(6), -isq2, va + (long)n * lr2, 0, vb + (long)n * lr2, 0, x11, ntrial))) return rc;
   } else {  // :1187-1193
