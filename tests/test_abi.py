@@ -47,6 +47,17 @@ def test_no_device_is_reported_not_faked(libpath):
     buf = (ctypes.c_double * 3)()
     lib.routec_fock_jk(buf, buf, ctypes.byref(nbf), ctypes.byref(nf), ctypes.byref(one), ctypes.byref(one), ctypes.byref(info))
     assert info.value != 0  # legacy seam declines -> caller runs native path (routec_bridge.F90:258-263)
+    # the sigma session declines the same way: no context -> init returns non-zero, iter reports info != 0
+    # (the driver then keeps its native mrsfcbc / int2 / mrsfmntoia path, tdhf_mrsf_energy.F90:655-665, 699-712)
+    n, na, nb_, kind = ctypes.c_int(2), ctypes.c_int(2), ctypes.c_int(0), ctypes.c_int(1)
+    mat = (ctypes.c_double * 4)()
+    lib.routec_sig_init.restype = ctypes.c_int
+    assert lib.routec_sig_init(ctypes.byref(n), mat, mat, mat, mat, ctypes.byref(na), ctypes.byref(nb_), ctypes.byref(kind)) != 0
+    info = ctypes.c_int(0)
+    nv = ctypes.c_int(1)
+    lib.routec_sig_iter(mat, ctypes.byref(nv), mat, ctypes.byref(info))
+    assert info.value != 0
+    lib.routec_sig_free()
 
 
 def test_sass_is_sm100a(libpath):
