@@ -150,7 +150,8 @@ def cpu_sample(bs, d_packed, sx, target_s, nthreads=0, cam=False):
     nthreads = nthreads or host_threads()
     """Oracle (C++/OpenMP restatement of int2_twoei, the reference's OpenMP CPU path) on a bounded,
     strided sample of the cost-sorted bra shell-pair list of the SAME workload."""
-    from oracle.oracle import Oracle, max_threads
+    from oracle.oracle import Oracle, max_threads, set_fast_rys
+    set_fast_rys(True)  # roots from polynomial tables, as stock OpenQP does for nroots <= 5 (timed baseline only)
     o = Oracle(bs)
     o.set_screening()
     npair = bs.nshell * (bs.nshell + 1) // 2
@@ -206,7 +207,8 @@ def emit(line: dict):
 def mrsf_cpu_sample(bs, d3, sx, target_s, nthreads=0, cutoff=5e-11):
     nthreads = nthreads or host_threads()
     """Oracle int2_mrsf_data_t build (tdhf_mrsf_lib.F90:218-333) on a strided sample of the bra shell-pair list."""
-    from oracle.oracle import Oracle
+    from oracle.oracle import Oracle, set_fast_rys
+    set_fast_rys(True)  # see cpu_sample
     o = Oracle(bs, cutoff)
     o.set_screening()
     npair = bs.nshell * (bs.nshell + 1) // 2
@@ -391,7 +393,7 @@ def run_reference(args):
             "config": (dict(workload_config(args, bs, W, sx, args.nvec), cutoff=args.cutoff) if args.workload in MRSF_WORKLOADS
                        else workload_config(args, bs, W, sx)),
             "cpu_baseline": {"value": val, "unit": "quartets/s", "cores": cores, "kind": "port",
-                             "note": "Rys-only C++/OpenMP port of int2_twoei; stock OpenQP (rotated-axis + libint) is faster",
+                             "note": "Rys-only C++/OpenMP port of int2_twoei, Rys roots from polynomial tables; stock OpenQP (rotated-axis s/p/d code, libint for f) is faster",
                              "sample": f"every {stride}-th bra shell pair of the cost-sorted list (int2.F90:864-921), "
                                        f"{quartets} quartets per {args.steps} steps"},
             "e2e": {"value": val, "unit": "quartets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -575,7 +577,7 @@ def main():
             line["cpu_baseline"] = {"value": r["quartets"] / r["seconds"], "unit": "quartets/s", "cores": r["cores"], "kind": "port",
                                     "sample": f"every {r['stride']}-th bra shell pair of the cost-sorted list, "
                                               f"{r['quartets']} quartets in {r['seconds']:.1f} s",
-                                    "note": "Rys-only C++/OpenMP port of int2_twoei (general Rys roots for every nroots); "
+                                    "note": "Rys-only C++/OpenMP port of int2_twoei, Rys roots from polynomial tables; "
                                             "stock OpenQP uses rotated-axis s/p/d code and libint for f and is faster"}
         emit(line)
     drv.clean()

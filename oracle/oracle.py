@@ -296,5 +296,11 @@ def rys(nroots: int, x: float):
     return u, w
 
 
+def set_fast_rys(on: bool):
+    """Timed CPU baseline only: roots/weights of nroots <= 7 from Chebyshev tables instead of the general Stieltjes
+    algorithm (the reference itself uses polynomial fits for nroots <= 5, rys.F90:45-2695).  Off for every parity test."""
+    lib().orc_set_fast_rys(C.c_int(1 if on else 0))
+
+
 def max_threads() -> int:
     return lib().orc_max_threads()

@@ -198,8 +198,40 @@ void golub_welsch(int n, double *a, double *b, double eps, double *wt) {
   for (int i = 0; i < n; i++) wt[i] = mu0 * wt[i] * wt[i];
 }
 
+// ---- optional table-driven roots, for the TIMED CPU baseline only (bench.py --impl reference / cpu_baseline) ----------
+// The reference evaluates nroots <= 5 from polynomial fits (rys.F90:45-2695), two orders of magnitude cheaper per X than
+// the general Stieltjes path restated above; those fit tables are not restated here.  With orc_set_fast_rys(1) the roots
+// and weights of nroots <= 7 are interpolated instead from the Chebyshev tables of tools/gen_rys_tables.py (100-digit
+// mpmath moments; unit X intervals, 12 terms, half-range Hermite asymptote beyond the table), so that the CPU arm of the
+// benchmark is not handicapped by the root finder.  The parity tests never enable it (the checker stays independent of
+// anything the CUDA path uses); tests/test_oracle_golden.py checks the two paths against each other.
+#include "../openqp_b200/csrc/rys_tables.inc"
+static int g_fast_rys = 0;
+static inline void rys_fast(double x, int nroots, double *u, double *w) {
+  const int R = nroots;
+  if (x >= (double)RYS_XMAX_H[R - 1]) {
+    const double xi = 1.0 / x, rs = std::sqrt(xi);
+    for (int i = 0; i < R; i++) {
+      const double r = RYS_HERM_R_H[R - 1][i] * xi;
+      u[i] = r / (1.0 - r);
+      w[i] = RYS_HERM_W_H[R - 1][i] * rs;
+    }
+    return;
+  }
+  const int iv = (int)x;
+  const double t = 2.0 * (x - (double)iv) - 1.0, t2 = 2.0 * t;
+  const double *c = RYS_TAB_H + RYS_OFF_H[R - 1] + (size_t)iv * (2 * R) * RYS_NCOEF;
+  for (int f = 0; f < 2 * R; f++, c += RYS_NCOEF) {  // c0 + sum_k c_k T_k(t), Clenshaw
+    double b1 = 0.0, b2 = 0.0;
+    for (int k = RYS_NCOEF - 1; k >= 1; k--) { const double b0 = t2 * b1 - b2 + c[k]; b2 = b1; b1 = b0; }
+    const double v = t * b1 - b2 + c[0];
+    if (f < R) u[f] = v / (1.0 - v); else w[f - R] = v;
+  }
+}
+
 // rys.F90:2697-2727; returns u = r/(1-r) and weights
 void rys_general(double x, int nroots, double *u, double *w) {
+  if (g_fast_rys && nroots <= RYS_MAXR) { rys_fast(x, nroots, u, w); return; }
   const RysTables &T = rys_tables();
   double r[MXRYS];
   if (x >= XASYMP[nroots - 1]) {
@@ -1190,6 +1222,8 @@ void orc_get_schwarz(void *h, double *out) {  // the matrix of the active pass
 }
 
 void orc_rys(int nroots, double x, double *u, double *w) { rys_general(x, nroots, u, w); }
+// table-driven roots for the timed CPU baseline (see rys_fast); 0 = the restated general algorithm (default, parity)
+void orc_set_fast_rys(int on) { g_fast_rys = on; }
 
 // one shell quartet (0-based shells); out(l,k,j,i) in ORIGINAL shell order i,j,k,l (l fastest), nout[4]
 int orc_eri_block(void *h, int i, int j, int k, int l, double *out, int *nout) {

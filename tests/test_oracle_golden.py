@@ -328,3 +328,29 @@ def test_oracle_eri_vs_mpmath_mcmurchie_davidson(oracle_mod):
         worst = max(worst, err)
         assert err < 1e-12, (q, [int(bs.am[s]) for s in q], err)
     print(f"oracle vs McMurchie-Davidson/mpmath: {len(MD_QUARTETS)} quartets, worst relative block error {worst:.1e}")
+
+
+def test_oracle_fast_rys_matches_general(oracle_mod):
+    """The table-driven roots that only the TIMED CPU baseline switches on (orc_set_fast_rys; bench.py cpu_baseline and
+    --impl reference) against the restated general algorithm: roots / weights to 1e-12 relative, a Fock build to 1e-12."""
+    rng = np.random.default_rng(0)
+    try:
+        for R in range(1, 8):
+            for x in np.concatenate([rng.uniform(0, 90, 60), [0.0, 1e-9, 38.999, 39.0, 74.999, 75.0, 200.0]]):
+                oracle_mod.set_fast_rys(False)
+                u0, w0 = oracle_mod.rys(R, float(x))
+                oracle_mod.set_fast_rys(True)
+                u1, w1 = oracle_mod.rys(R, float(x))
+                o0, o1 = np.argsort(u0), np.argsort(u1)
+                assert np.abs(u1[o1] / u0[o0] - 1).max() < 1e-12 and np.abs(w1[o1] / w0[o0] - 1).max() < 1e-12, (R, x)
+        bs = B.BasisSet(B.water(), "cc-pvtz")
+        o = oracle_mod.Oracle(bs)
+        o.set_screening()
+        d = pack(random_sym_density(bs.nbf, 3))
+        oracle_mod.set_fast_rys(False)
+        f0 = o.fock(d)[0]
+        oracle_mod.set_fast_rys(True)
+        f1 = o.fock(d)[0]
+        assert np.abs(f1 - f0).max() < 1e-12 * max(1.0, np.abs(f0).max())
+    finally:
+        oracle_mod.set_fast_rys(False)
