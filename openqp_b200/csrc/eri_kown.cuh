@@ -27,7 +27,7 @@ __host__ __device__ constexpr int kown_kpl_override() {
   // |dp) kets (18 components) on the (dp| and (dd| bras: two per lane = 9 lanes x 3 quartets per warp instead of 18 lanes x 1
   // ((dp|dp) 48.5 -> 44.2 ms, (dd|dp) 24.6 -> 21.4 ms)
   if (LC == 2 && LD == 1 && ((LA == 2 && LB == 1) || (LA == 2 && LB == 2))) return 2;
-  return (LA == 3 && LB == 1) ? 0 : ((LA == 3 && LB == 2) ? 1 : 1);
+  return (LA == 3 && LB == 1) ? 0 : 1;  // (fp| bra: the heuristic below (two where they divide evenly); everything else: one
 }
 
 template <int LA, int LB, int LC, int LD, int PV>
