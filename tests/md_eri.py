@@ -78,8 +78,11 @@ def hermite_R(L, alpha, X, Y, Z):
     return R
 
 
-def shell_quartet(bs, i, j, k, l):
-    """(ij|kl) block [ni][nj][nk][nl] of contracted, unit-normalised CARTESIAN shells of BasisSet `bs` (as floats)."""
+def shell_quartet(bs, i, j, k, l, mu=None):
+    """(ij|kl) block [ni][nj][nk][nl] of contracted, unit-normalised CARTESIAN shells of BasisSet `bs` (as floats).
+    mu: the operator is erf(mu r12)/r12 (the range-separated CAM pass, int_rys.F90:179-181, 225-227) instead of 1/r12:
+    with 1/r = 2/sqrt(pi) int_0^inf exp(-u^2 r^2) du cut at u = mu, the Boys argument alpha = pq/(p+q) becomes
+    alpha' = alpha mu^2 / (alpha + mu^2) and the integral picks up the factor sqrt(alpha'/alpha)."""
     sh = (i, j, k, l)
     L = [int(bs.am[s]) for s in sh]
     cen = [[mp.mpf(float(x)) for x in bs.centers[s]] for s in sh]
@@ -92,10 +95,16 @@ def shell_quartet(bs, i, j, k, l):
         P = [(a * cen[0][x] + b * cen[1][x]) / p for x in range(3)]
         Q = [(c * cen[2][x] + d * cen[3][x]) / q for x in range(3)]
         alpha = p * q / (p + q)
+        att = mp.mpf(1)
+        if mu is not None:
+            m2 = mp.mpf(mu) ** 2
+            alpha_eff = alpha * m2 / (alpha + m2)
+            att = mp.sqrt(alpha_eff / alpha)
+            alpha = alpha_eff
         R = hermite_R(Ltot, alpha, P[0] - Q[0], P[1] - Q[1], P[2] - Q[2])
         Eab = [hermite_E(L[0], L[1], a, b, cen[0][x], cen[1][x]) for x in range(3)]
         Ecd = [hermite_E(L[2], L[3], c, d, cen[2][x], cen[3][x]) for x in range(3)]
-        pref = 2 * mp.pi ** (mp.mpf(5) / 2) / (p * q * mp.sqrt(p + q)) * ca * cb * cc * cd
+        pref = 2 * mp.pi ** (mp.mpf(5) / 2) / (p * q * mp.sqrt(p + q)) * ca * cb * cc * cd * att
         for ia, A in enumerate(comps[0]):
             for ib, B in enumerate(comps[1]):
                 ex, ey, ez = Eab[0][(A[0], B[0])], Eab[1][(A[1], B[1])], Eab[2][(A[2], B[2])]

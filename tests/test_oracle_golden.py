@@ -354,3 +354,31 @@ def test_oracle_fast_rys_matches_general(oracle_mod):
         assert np.abs(f1 - f0).max() < 1e-12 * max(1.0, np.abs(f0).max())
     finally:
         oracle_mod.set_fast_rys(False)
+
+
+def test_oracle_attenuated_eri_vs_mpmath_mcmurchie_davidson(oracle_mod):
+    """The Erf-attenuated integrals of the CAM second pass (int_rys.F90:179-181, 225-227: ab = zeta + eta + zeta eta / mu^2)
+    for d / f quartets on up to four centres against the independent McMurchie-Davidson evaluation with the operator
+    erf(mu r12) / r12 (tests/md_eri.py): pins the range-separated integrals beyond the contracted (ss|ss) closed form."""
+    import md_eri
+    bs = B.BasisSet(B.water_dimer(), "cc-pvtz", spherical=False)
+    o = oracle_mod.Oracle(bs)
+    o.set_screening()
+    mu = 0.33  # CAM-B3LYP
+    o.set_attenuation(mu)
+    try:
+        worst = 0.0
+        for q in [(9, 15, 31, 21), (9, 9, 15, 13), (31, 26, 21, 16), (7, 0, 26, 22)]:
+            i, j, k, l = q
+            ref = np.array(md_eri.shell_quartet(bs, *q, mu=mu))
+            blk = o.eri_block(max(i, j), min(i, j), max(k, l), min(k, l))
+            if i < j:
+                blk = blk.transpose(1, 0, 2, 3)
+            if k < l:
+                blk = blk.transpose(0, 1, 3, 2)
+            err = np.abs(blk - ref).max() / np.abs(ref).max()
+            worst = max(worst, err)
+            assert err < 1e-12, (q, err)
+        print(f"attenuated integrals, oracle vs McMurchie-Davidson/mpmath: worst relative block error {worst:.1e}")
+    finally:
+        o.set_attenuation(0.0)
